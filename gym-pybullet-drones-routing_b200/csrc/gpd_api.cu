@@ -1,0 +1,535 @@
+// gpd_api.cu — the C ABI of libgpd_b200 (include/gpd.h): handle management, argument checking,
+// dispatch on precision.  No compute happens on the host: without a CUDA device every entry point
+// that would compute returns GPD_ERR_NO_DEVICE (there is no CPU fallback).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "gpd_internal.h"
+
+namespace gpd {
+cudaError_t launch_stats(const double* slots, int64_t nslots, double* out8, int clear, double* slots_mut, cudaStream_t st);
+}
+
+using namespace gpd;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? GPD_ERR_NO_DEVICE : GPD_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(_e));                           \
+    } while (0)
+
+struct gpd_sim {
+    gpd_config cfg;
+    int A, B, W, S;
+    int64_t D;
+    LaunchCfg lc;
+    std::vector<void*> allocs;
+    StepArgs<float> a32;
+    StepArgs<double> a64;
+    std::vector<double> target_host;
+    // host-buffer path (gpd_step_host): device I/O buffers + obs ping-pong, allocated lazily
+    void* h_act = nullptr;
+    void* h_obs[2] = { nullptr, nullptr };
+    void* h_rew = nullptr;
+    uint8_t* h_term = nullptr;
+    uint8_t* h_trunc = nullptr;
+    float* h_tkin = nullptr;
+    int h_cur = 0;
+    bool h_has_prev = false;
+    double* stats_out = nullptr;
+};
+
+static int action_width(int act)
+{
+    switch (act) {
+    case GPD_ACT_RPM: case GPD_ACT_VEL: case GPD_ACT_CTRL_RPM: return 4;
+    case GPD_ACT_PID: return 3;
+    case GPD_ACT_ONE_D_RPM: case GPD_ACT_ONE_D_PID: return 1;
+    default: return -1;
+    }
+}
+
+template <typename R>
+static void fill_drone(const gpd_drone_params& p, DevDrone<R>& d)
+{
+    d.model = p.model;
+    d.M = (R)p.M; d.L = (R)p.L; d.ARM = (R)(p.L / std::sqrt(2.0));
+    d.KF = (R)p.KF; d.KM = (R)p.KM;
+    for (int k = 0; k < 3; ++k) { d.J[k] = (R)p.J[k]; d.JINV[k] = (R)p.J_INV[k]; d.DRAG[k] = (R)p.DRAG_COEFF[k]; }
+    d.GRAVITY = (R)p.GRAVITY; d.MAX_RPM = (R)p.MAX_RPM;
+    d.GND_EFF_COEFF = (R)p.GND_EFF_COEFF; d.PROP_RADIUS = (R)p.PROP_RADIUS; d.GND_EFF_H_CLIP = (R)p.GND_EFF_H_CLIP;
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 3; ++k) d.ROTOR[i][k] = (R)p.ROTOR_XYZ[i][k];
+    d.DW1 = (R)p.DW_COEFF_1; d.DW2 = (R)p.DW_COEFF_2; d.DW3 = (R)p.DW_COEFF_3;
+    d.KF_d = p.KF; d.KM_d = p.KM; d.GRAVITY_d = p.GRAVITY; d.L_d = p.L; d.ARM_d = p.L / std::sqrt(2.0);
+    d.HOVER_RPM_d = p.HOVER_RPM; d.MAX_RPM_d = p.MAX_RPM;
+}
+
+template <typename R>
+static void fill_pid(const gpd_pid_params& p, DevPid<R>& c)
+{
+    for (int k = 0; k < 3; ++k) {
+        c.P_FOR[k] = (R)p.P_FOR[k]; c.I_FOR[k] = (R)p.I_FOR[k]; c.D_FOR[k] = (R)p.D_FOR[k];
+        c.P_TOR[k] = (R)p.P_TOR[k]; c.I_TOR[k] = (R)p.I_TOR[k]; c.D_TOR[k] = (R)p.D_TOR[k];
+    }
+    c.PWM2RPM_SCALE = (R)p.PWM2RPM_SCALE; c.PWM2RPM_CONST = (R)p.PWM2RPM_CONST;
+    c.MIN_PWM = (R)p.MIN_PWM; c.MAX_PWM = (R)p.MAX_PWM;
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 3; ++k) c.MIXER[i][k] = (R)p.MIXER[i][k];
+    c.GRAVITY = (R)p.GRAVITY; c.KF4 = (R)(4 * p.KF);
+}
+
+static size_t smem_bytes(bool f64, bool ctrl, bool multi, int DPB, int EPB)
+{
+    size_t rs = f64 ? 8 : 4;
+    size_t stage = ctrl ? (size_t)DPB * 20 * rs : (size_t)DPB * 12 * 4;
+    size_t b = (stage + 15) & ~size_t(15);
+    if (multi) b += (size_t)DPB * 3 * rs + (size_t)DPB * 2 * rs + (size_t)DPB * 4 + (size_t)EPB * 2 * 4;
+    b += 32;
+    return (b + 15) & ~size_t(15);
+}
+
+template <typename T>
+static int dev_alloc(gpd_sim* s, T** p, size_t count, bool zero = true)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) return fail(GPD_ERR_ALLOC, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    if (zero) {
+        e = cudaMemset(q, 0, count * sizeof(T) ? count * sizeof(T) : 16);
+        if (e != cudaSuccess) return fail(GPD_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return GPD_OK;
+}
+
+// closed forms used to build the initial poses on the host (BaseAviary.py:488: p.getQuaternionFromEuler)
+static void host_quat_from_euler(const double rpy[3], double q[4])
+{
+    double hr = rpy[0] * 0.5, hp = rpy[1] * 0.5, hy = rpy[2] * 0.5;
+    double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+    double x = sr * cp * cy - cr * sp * sy, y = cr * sp * cy + sr * cp * sy;
+    double z = cr * cp * sy - sr * sp * cy, w = cr * cp * cy + sr * sp * sy;
+    double n = std::sqrt(x * x + y * y + z * z + w * w);
+    q[0] = x / n; q[1] = y / n; q[2] = z / n; q[3] = w / n;
+}
+
+template <typename R>
+static int upload_init(gpd_sim* s, StepArgs<R>& a, const double* xyz, const double* rpy, int per_env)
+{
+    using V = typename Vec4<R>::type;
+    int64_t n = per_env ? s->D : s->cfg.num_drones;
+    std::vector<V> hp((size_t)n), hq((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+        double q[4];
+        host_quat_from_euler(rpy + 3 * k, q);
+        hp[k].x = (R)xyz[3 * k]; hp[k].y = (R)xyz[3 * k + 1]; hp[k].z = (R)xyz[3 * k + 2]; hp[k].w = (R)0;
+        hq[k].x = (R)q[0]; hq[k].y = (R)q[1]; hq[k].z = (R)q[2]; hq[k].w = (R)q[3];
+    }
+    V* dp = nullptr; V* dq = nullptr;
+    int rc;
+    if ((rc = dev_alloc(s, &dp, (size_t)n, false))) return rc;
+    if ((rc = dev_alloc(s, &dq, (size_t)n, false))) return rc;
+    CU(cudaMemcpy(dp, hp.data(), sizeof(V) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dq, hq.data(), sizeof(V) * n, cudaMemcpyHostToDevice));
+    a.p.init_pos = dp; a.p.init_quat = dq; a.init_per_env = per_env ? 1 : 0;
+    return GPD_OK;
+}
+
+template <typename R>
+static int build_args(gpd_sim* s, StepArgs<R>& a)
+{
+    using V = typename Vec4<R>::type;
+    const gpd_config& c = s->cfg;
+    memset(&a, 0, sizeof a);
+    a.D = s->D; a.E = c.num_envs; a.N = c.num_drones; a.S = s->S; a.A = s->A; a.B = s->B; a.W = s->W;
+    a.env_kind = c.env_kind; a.action_type = c.action_type; a.phy = c.physics_flags; a.auto_reset = c.auto_reset;
+    a.dt = (R)(1.0 / c.pyb_freq); a.ctrl_dt = (R)(1.0 / c.ctrl_freq); a.speed_limit = (R)c.speed_limit;
+    a.pyb_freq = (double)c.pyb_freq; a.episode_len = c.episode_len_sec;
+    fill_drone(c.drone, a.drone);
+    fill_pid(c.pid, a.pid);
+    int rc;
+    V *sP, *sQ, *sV, *av, *rp; R* wz;
+    if ((rc = dev_alloc(s, &sP, (size_t)s->D))) return rc;
+    if ((rc = dev_alloc(s, &sQ, (size_t)s->D))) return rc;
+    if ((rc = dev_alloc(s, &sV, (size_t)s->D))) return rc;
+    if ((rc = dev_alloc(s, &wz, (size_t)s->D))) return rc;
+    if ((rc = dev_alloc(s, &av, (size_t)s->D))) return rc;
+    if ((rc = dev_alloc(s, &rp, (size_t)s->D))) return rc;
+    a.p.sP = sP; a.p.sQ = sQ; a.p.sV = sV; a.p.sWz = wz; a.p.aux_av = av; a.p.aux_rpm = rp;
+    const bool pidfam = c.action_type == GPD_ACT_PID || c.action_type == GPD_ACT_VEL || c.action_type == GPD_ACT_ONE_D_PID;
+    R* pid = nullptr;
+    if ((rc = dev_alloc(s, &pid, (size_t)s->D * 9))) return rc;      // also used by gpd_rollout_pid
+    (void)pidfam;
+    a.p.pid = pid;
+    int32_t* cnt;
+    if ((rc = dev_alloc(s, &cnt, (size_t)c.num_envs))) return rc;
+    a.p.counter = cnt;
+    if (c.auto_reset) {
+        float* er; int32_t* el; double* slots;
+        if ((rc = dev_alloc(s, &er, (size_t)c.num_envs))) return rc;
+        if ((rc = dev_alloc(s, &el, (size_t)c.num_envs))) return rc;
+        if ((rc = dev_alloc(s, &slots, (size_t)s->lc.grid * 8))) return rc;
+        std::vector<double> init((size_t)s->lc.grid * 8, 0.0);
+        for (int64_t k = 0; k < s->lc.grid; ++k) { init[k * 8 + 4] = 1e300; init[k * 8 + 5] = -1e300; }
+        CU(cudaMemcpy(slots, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice));
+        a.p.ep_ret = er; a.p.ep_len = el; a.p.stat_slots = slots;
+    }
+    // targets
+    std::vector<V> ht((size_t)c.num_drones);
+    for (int k = 0; k < c.num_drones; ++k) {
+        ht[k].x = (R)s->target_host[3 * k]; ht[k].y = (R)s->target_host[3 * k + 1]; ht[k].z = (R)s->target_host[3 * k + 2]; ht[k].w = (R)0;
+    }
+    V* dt_ = nullptr;
+    if ((rc = dev_alloc(s, &dt_, (size_t)c.num_drones, false))) return rc;
+    CU(cudaMemcpy(dt_, ht.data(), sizeof(V) * c.num_drones, cudaMemcpyHostToDevice));
+    a.p.target = dt_;
+    a.DPB = s->lc.threads >= c.num_drones ? (s->lc.threads / c.num_drones) * c.num_drones : c.num_drones;
+    a.EPB = a.DPB / c.num_drones;
+    // default initial poses, BaseAviary.py:194-207
+    std::vector<double> xyz((size_t)c.num_drones * 3), rpy((size_t)c.num_drones * 3, 0.0);
+    for (int k = 0; k < c.num_drones; ++k) {
+        xyz[3 * k] = k * 4 * c.drone.L; xyz[3 * k + 1] = k * 4 * c.drone.L;
+        xyz[3 * k + 2] = c.drone.COLLISION_H / 2 - c.drone.COLLISION_Z_OFFSET + .1;
+    }
+    return upload_init(s, a, xyz.data(), rpy.data(), 0);
+}
+
+extern "C" {
+
+int gpd_version(void) { return GPD_VERSION; }
+const char* gpd_last_error(void) { return g_err; }
+
+int gpd_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(GPD_ERR_NO_DEVICE, "cudaGetDeviceCount failed: %s (no CPU fallback exists)", cudaGetErrorString(e));
+    return n;
+}
+
+int gpd_create(const gpd_config* cfg, gpd_sim** out)
+{
+    if (!cfg || !out) return fail(GPD_ERR_INVALID, "gpd_create: null argument");
+    *out = nullptr;
+    if (cfg->num_envs < 1) return fail(GPD_ERR_INVALID, "num_envs must be >= 1");
+    if (cfg->num_drones < 1 || cfg->num_drones > GPD_MAX_DRONES_PER_ENV)
+        return fail(GPD_ERR_INVALID, "num_drones must be in [1, %d]", GPD_MAX_DRONES_PER_ENV);
+    if (cfg->pyb_freq < 1 || cfg->ctrl_freq < 1 || cfg->pyb_freq % cfg->ctrl_freq != 0)
+        return fail(GPD_ERR_INVALID, "pyb_freq is not divisible by ctrl_freq");          // BaseAviary.py:79-80
+    if (cfg->precision != GPD_F32 && cfg->precision != GPD_F64) return fail(GPD_ERR_INVALID, "bad precision");
+    int A = action_width(cfg->action_type);
+    if (A < 0) return fail(GPD_ERR_INVALID, "bad action_type");
+    const bool ctrl = cfg->env_kind == GPD_ENV_CTRL;
+    if (ctrl != (cfg->action_type == GPD_ACT_CTRL_RPM))
+        return fail(GPD_ERR_INVALID, "GPD_ACT_CTRL_RPM goes with GPD_ENV_CTRL and only with it");
+    if (cfg->env_kind == GPD_ENV_HOVER && cfg->num_drones != 1) return fail(GPD_ERR_INVALID, "HoverAviary is single-drone");
+    if (cfg->env_kind < GPD_ENV_CTRL || cfg->env_kind > GPD_ENV_MULTIHOVER) return fail(GPD_ERR_INVALID, "bad env_kind");
+    if (!ctrl && !cfg->target_pos) return fail(GPD_ERR_INVALID, "target_pos is required for the RL envs");
+    const bool pidfam = cfg->action_type == GPD_ACT_PID || cfg->action_type == GPD_ACT_VEL || cfg->action_type == GPD_ACT_ONE_D_PID;
+    if (pidfam && cfg->drone.model == GPD_RACE)
+        return fail(GPD_ERR_INVALID, "no controller is available for the specified drone_model");   // BaseRLAviary.py:77-78
+    if ((cfg->physics_flags & ~(GPD_PHY_GND | GPD_PHY_DRAG | GPD_PHY_DW)) != 0) return fail(GPD_ERR_INVALID, "bad physics_flags");
+    if (cfg->threads_per_block != 0 && (cfg->threads_per_block % 32 != 0 || cfg->threads_per_block > 256 || cfg->threads_per_block < 32))
+        return fail(GPD_ERR_INVALID, "threads_per_block must be a multiple of 32 in [32, 256]");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(GPD_ERR_NO_DEVICE, "CUDA device %d not available (%d visible)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+
+    gpd_sim* s = new (std::nothrow) gpd_sim();
+    if (!s) return fail(GPD_ERR_ALLOC, "out of host memory");
+    s->cfg = *cfg;
+    s->A = A;
+    s->B = ctrl ? 0 : cfg->ctrl_freq / 2;                                               // BaseRLAviary.py:66
+    s->W = ctrl ? 20 : 12 + A * s->B;
+    s->S = cfg->pyb_freq / cfg->ctrl_freq;                                              // BaseAviary.py:81
+    s->D = cfg->num_envs * (int64_t)cfg->num_drones;
+    s->target_host.assign((size_t)cfg->num_drones * 3, 0.0);
+    if (cfg->target_pos) memcpy(s->target_host.data(), cfg->target_pos, sizeof(double) * cfg->num_drones * 3);
+    s->cfg.target_pos = nullptr;
+    int T = cfg->threads_per_block ? cfg->threads_per_block : 128;
+    int N = cfg->num_drones;
+    int DPB = T >= N ? (T / N) * N : N;
+    if (DPB > T) T = (DPB + 31) / 32 * 32;
+    int EPB = DPB / N;
+    s->lc.threads = T;
+    s->lc.grid = (cfg->num_envs + EPB - 1) / EPB;
+    s->lc.smem = smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
+    if (s->lc.grid > 0x7fffffffLL) { delete s; return fail(GPD_ERR_INVALID, "too many envs for one launch"); }
+    int rc = cfg->precision == GPD_F64 ? build_args(s, s->a64) : build_args(s, s->a32);
+    if (rc == GPD_OK) { cudaError_t e = cudaMalloc((void**)&s->stats_out, 8 * sizeof(double)); if (e != cudaSuccess) rc = fail(GPD_ERR_ALLOC, "cudaMalloc failed"); }
+    if (rc != GPD_OK) { gpd_destroy(s); return rc; }
+    // start in the reset state (BaseAviary.__init__ ends with _housekeeping + _updateAndStoreKinematicInformation)
+    rc = gpd_reset(s, nullptr, nullptr, nullptr, nullptr);
+    if (rc == GPD_OK) { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) rc = fail(GPD_ERR_CUDA, "initial reset failed: %s", cudaGetErrorString(e)); }
+    if (rc != GPD_OK) { gpd_destroy(s); return rc; }
+    *out = s;
+    return GPD_OK;
+}
+
+void gpd_destroy(gpd_sim* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    for (void* p : s->allocs) cudaFree(p);
+    cudaFree(s->h_act); cudaFree(s->h_obs[0]); cudaFree(s->h_obs[1]); cudaFree(s->h_rew);
+    cudaFree(s->h_term); cudaFree(s->h_trunc); cudaFree(s->h_tkin); cudaFree(s->stats_out);
+    delete s;
+}
+
+int gpd_obs_width(const gpd_sim* s) { return s ? s->W : fail(GPD_ERR_INVALID, "null handle"); }
+int gpd_action_width(const gpd_sim* s) { return s ? s->A : fail(GPD_ERR_INVALID, "null handle"); }
+int gpd_substeps(const gpd_sim* s) { return s ? s->S : fail(GPD_ERR_INVALID, "null handle"); }
+
+int gpd_set_init_poses(gpd_sim* s, const double* xyz, const double* rpy, int per_env)
+{
+    if (!s || !xyz || !rpy) return fail(GPD_ERR_INVALID, "gpd_set_init_poses: null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    return s->cfg.precision == GPD_F64 ? upload_init(s, s->a64, xyz, rpy, per_env) : upload_init(s, s->a32, xyz, rpy, per_env);
+}
+
+int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* obs_out, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    if (obs_out && obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->cfg.precision == GPD_F64) {
+        StepArgs<double> a = s->a64;
+        a.reset_mask = env_mask; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out;
+        CU(launch_reset<double>(a, s->lc, st));
+    } else {
+        StepArgs<float> a = s->a32;
+        a.reset_mask = env_mask; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out;
+        CU(launch_reset<float>(a, s->lc, st));
+    }
+    return GPD_OK;
+}
+
+int gpd_step(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_out,
+             void* reward, uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    if (!actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step: actions and obs_out are required");
+    if (obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->cfg.precision == GPD_F64) {
+        StepArgs<double> a = s->a64;
+        a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
+        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin;
+        CU(launch_step<double>(a, s->lc, st));
+    } else {
+        StepArgs<float> a = s->a32;
+        a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
+        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin;
+        CU(launch_step<float>(a, s->lc, st));
+    }
+    return GPD_OK;
+}
+
+static int ensure_host_path(gpd_sim* s)
+{
+    if (s->h_obs[0]) return GPD_OK;
+    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
+    const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
+    size_t act_b = (size_t)s->D * s->A * (ctrl ? rs : 4), obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
+    CU(cudaMalloc(&s->h_act, act_b));
+    CU(cudaMalloc(&s->h_obs[0], obs_b));
+    CU(cudaMalloc(&s->h_obs[1], obs_b));
+    CU(cudaMalloc(&s->h_rew, (size_t)s->cfg.num_envs * rs));
+    CU(cudaMalloc((void**)&s->h_term, (size_t)s->cfg.num_envs));
+    CU(cudaMalloc((void**)&s->h_trunc, (size_t)s->cfg.num_envs));
+    CU(cudaMalloc((void**)&s->h_tkin, (size_t)s->D * 12 * sizeof(float)));
+    CU(cudaMemset(s->h_tkin, 0, (size_t)s->D * 12 * sizeof(float)));
+    return GPD_OK;
+}
+
+int gpd_step_host(gpd_sim* s, const void* actions, void* obs_out, void* reward,
+                  uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream)
+{
+    if (!s || !actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step_host: null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    int rc = ensure_host_path(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
+    const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
+    size_t act_b = (size_t)s->D * s->A * (ctrl ? rs : 4), obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
+    CU(cudaMemcpyAsync(s->h_act, actions, act_b, cudaMemcpyHostToDevice, st));
+    int nxt = s->h_cur ^ 1;
+    rc = gpd_step(s, s->h_act, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], s->h_rew, s->h_term, s->h_trunc,
+                  terminal_kin ? s->h_tkin : nullptr, stream);
+    if (rc) return rc;
+    s->h_cur = nxt; s->h_has_prev = true;
+    CU(cudaMemcpyAsync(obs_out, s->h_obs[nxt], obs_b, cudaMemcpyDeviceToHost, st));
+    if (reward) CU(cudaMemcpyAsync(reward, s->h_rew, (size_t)s->cfg.num_envs * rs, cudaMemcpyDeviceToHost, st));
+    if (terminated) CU(cudaMemcpyAsync(terminated, s->h_term, (size_t)s->cfg.num_envs, cudaMemcpyDeviceToHost, st));
+    if (truncated) CU(cudaMemcpyAsync(truncated, s->h_trunc, (size_t)s->cfg.num_envs, cudaMemcpyDeviceToHost, st));
+    if (terminal_kin) CU(cudaMemcpyAsync(terminal_kin, s->h_tkin, (size_t)s->D * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GPD_OK;
+}
+
+int gpd_reset_host(gpd_sim* s, const uint8_t* env_mask, void* obs_out, void* stream)
+{
+    if (!s || !obs_out) return fail(GPD_ERR_INVALID, "gpd_reset_host: null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    int rc = ensure_host_path(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
+    const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
+    size_t obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
+    uint8_t* dmask = nullptr;
+    if (env_mask) {
+        CU(cudaMalloc((void**)&dmask, (size_t)s->cfg.num_envs));
+        CU(cudaMemcpyAsync(dmask, env_mask, (size_t)s->cfg.num_envs, cudaMemcpyHostToDevice, st));
+    }
+    int nxt = s->h_cur ^ 1;
+    rc = gpd_reset(s, dmask, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], stream);
+    if (rc == GPD_OK) {
+        s->h_cur = nxt; s->h_has_prev = true;
+        cudaError_t e = cudaMemcpyAsync(obs_out, s->h_obs[nxt], obs_b, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(GPD_ERR_CUDA, "gpd_reset_host copy failed: %s", cudaGetErrorString(e));
+    }
+    if (dmask) cudaFree(dmask);
+    return rc;
+}
+
+int gpd_get_state(gpd_sim* s, void* state20, void* rpy_rates, void* pid_state, int32_t* step_counter, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(s->cfg.device));
+    if (s->cfg.precision == GPD_F64)
+        CU(launch_get_state<double>(s->a64, (double*)state20, (double*)rpy_rates, (double*)pid_state, step_counter, (cudaStream_t)stream));
+    else
+        CU(launch_get_state<float>(s->a32, (float*)state20, (float*)rpy_rates, (float*)pid_state, step_counter, (cudaStream_t)stream));
+    return GPD_OK;
+}
+
+int gpd_set_state(gpd_sim* s, const void* state20, const void* rpy_rates, const void* pid_state,
+                  const int32_t* step_counter, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(s->cfg.device));
+    if (s->cfg.precision == GPD_F64)
+        CU(launch_set_state<double>(s->a64, (const double*)state20, (const double*)rpy_rates, (const double*)pid_state, step_counter, (cudaStream_t)stream));
+    else
+        CU(launch_set_state<float>(s->a32, (const float*)state20, (const float*)rpy_rates, (const float*)pid_state, step_counter, (cudaStream_t)stream));
+    return GPD_OK;
+}
+
+int gpd_pid_compute(int device, int precision, const gpd_pid_params* pid, int64_t n, double control_timestep,
+                    const void* cur_pos, const void* cur_quat, const void* cur_vel, const void* target_pos,
+                    const void* target_rpy, const void* target_vel, const void* target_rpy_rates,
+                    void* pid_state, void* rpm_out, void* pos_e_out, void* yaw_e_out, void* stream)
+{
+    if (!pid || !cur_pos || !cur_quat || !cur_vel || !target_pos || !pid_state || !rpm_out || n < 0)
+        return fail(GPD_ERR_INVALID, "gpd_pid_compute: null argument");
+    if (n == 0) return GPD_OK;
+    CU(cudaSetDevice(device));
+    if (precision == GPD_F64) {
+        DevPid<double> c; fill_pid(*pid, c);
+        CU(launch_pid<double>(c, n, control_timestep, (const double*)cur_pos, (const double*)cur_quat, (const double*)cur_vel,
+                              (const double*)target_pos, (const double*)target_rpy, (const double*)target_vel,
+                              (const double*)target_rpy_rates, (double*)pid_state, (double*)rpm_out, (double*)pos_e_out,
+                              (double*)yaw_e_out, (cudaStream_t)stream));
+    } else if (precision == GPD_F32) {
+        DevPid<float> c; fill_pid(*pid, c);
+        CU(launch_pid<float>(c, n, (float)control_timestep, (const float*)cur_pos, (const float*)cur_quat, (const float*)cur_vel,
+                             (const float*)target_pos, (const float*)target_rpy, (const float*)target_vel,
+                             (const float*)target_rpy_rates, (float*)pid_state, (float*)rpm_out, (float*)pos_e_out,
+                             (float*)yaw_e_out, (cudaStream_t)stream));
+    } else return fail(GPD_ERR_INVALID, "bad precision");
+    return GPD_OK;
+}
+
+int gpd_force_ground_effect(int device, int precision, const gpd_drone_params* d, int64_t n, const void* rpm,
+                            const void* pos, const void* quat, void* out, uint8_t* applied, void* stream)
+{
+    if (!d || !rpm || !pos || !quat || !out || n < 0) return fail(GPD_ERR_INVALID, "gpd_force_ground_effect: null argument");
+    if (n == 0) return GPD_OK;
+    CU(cudaSetDevice(device));
+    if (precision == GPD_F64) { DevDrone<double> P; fill_drone(*d, P);
+        CU(launch_ground_effect<double>(P, n, (const double*)rpm, (const double*)pos, (const double*)quat, (double*)out, applied, (cudaStream_t)stream)); }
+    else { DevDrone<float> P; fill_drone(*d, P);
+        CU(launch_ground_effect<float>(P, n, (const float*)rpm, (const float*)pos, (const float*)quat, (float*)out, applied, (cudaStream_t)stream)); }
+    return GPD_OK;
+}
+
+int gpd_force_drag(int device, int precision, const gpd_drone_params* d, int64_t n, const void* rpm,
+                   const void* quat, const void* vel, void* out, void* stream)
+{
+    if (!d || !rpm || !quat || !vel || !out || n < 0) return fail(GPD_ERR_INVALID, "gpd_force_drag: null argument");
+    if (n == 0) return GPD_OK;
+    CU(cudaSetDevice(device));
+    if (precision == GPD_F64) { DevDrone<double> P; fill_drone(*d, P);
+        CU(launch_drag<double>(P, n, (const double*)rpm, (const double*)quat, (const double*)vel, (double*)out, (cudaStream_t)stream)); }
+    else { DevDrone<float> P; fill_drone(*d, P);
+        CU(launch_drag<float>(P, n, (const float*)rpm, (const float*)quat, (const float*)vel, (float*)out, (cudaStream_t)stream)); }
+    return GPD_OK;
+}
+
+int gpd_force_downwash(int device, int precision, const gpd_drone_params* d, int64_t num_envs, int32_t num_drones,
+                       const void* pos, void* out, void* stream)
+{
+    if (!d || !pos || !out || num_envs < 0 || num_drones < 1) return fail(GPD_ERR_INVALID, "gpd_force_downwash: bad argument");
+    if (num_envs == 0) return GPD_OK;
+    CU(cudaSetDevice(device));
+    if (precision == GPD_F64) { DevDrone<double> P; fill_drone(*d, P);
+        CU(launch_downwash<double>(P, num_envs, num_drones, (const double*)pos, (double*)out, (cudaStream_t)stream)); }
+    else { DevDrone<float> P; fill_drone(*d, P);
+        CU(launch_downwash<float>(P, num_envs, num_drones, (const float*)pos, (float*)out, (cudaStream_t)stream)); }
+    return GPD_OK;
+}
+
+int gpd_rollout_pid(gpd_sim* s, int32_t n_ctrl_steps, const void* waypoints, int32_t n_wp,
+                    int32_t* wp_counters, void* action, void* stream)
+{
+    if (!s || !waypoints || !wp_counters || !action || n_wp < 1 || n_ctrl_steps < 0)
+        return fail(GPD_ERR_INVALID, "gpd_rollout_pid: bad argument");
+    if (s->cfg.env_kind != GPD_ENV_CTRL) return fail(GPD_ERR_INVALID, "gpd_rollout_pid needs the Ctrl env");
+    if (s->cfg.drone.model == GPD_RACE) return fail(GPD_ERR_INVALID, "DSLPIDControl requires CF2X or CF2P");
+    if (s->cfg.physics_flags & GPD_PHY_DW) return fail(GPD_ERR_INVALID, "gpd_rollout_pid does not support downwash");
+    CU(cudaSetDevice(s->cfg.device));
+    if (s->cfg.precision == GPD_F64)
+        CU(launch_rollout_pid<double>(s->a64, n_ctrl_steps, (const double*)waypoints, n_wp, wp_counters, (double*)action, (cudaStream_t)stream));
+    else
+        CU(launch_rollout_pid<float>(s->a32, n_ctrl_steps, (const float*)waypoints, n_wp, wp_counters, (float*)action, (cudaStream_t)stream));
+    return GPD_OK;
+}
+
+int gpd_episode_stats(gpd_sim* s, double out[8], int clear, void* stream)
+{
+    if (!s || !out) return fail(GPD_ERR_INVALID, "gpd_episode_stats: null argument");
+    for (int k = 0; k < 8; ++k) out[k] = 0.0;
+    if (!s->cfg.auto_reset) return fail(GPD_ERR_INVALID, "episode statistics are kept only with auto_reset");
+    CU(cudaSetDevice(s->cfg.device));
+    double* slots = s->cfg.precision == GPD_F64 ? s->a64.p.stat_slots : s->a32.p.stat_slots;
+    CU(launch_stats(slots, s->lc.grid, s->stats_out, clear, slots, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(out, s->stats_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (out[0] == 0.0) { out[4] = 0.0; out[5] = 0.0; }
+    return GPD_OK;
+}
+
+}  // extern "C"

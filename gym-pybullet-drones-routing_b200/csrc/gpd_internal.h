@@ -1,0 +1,113 @@
+// gpd_internal.h — host/device shared declarations of libgpd_b200 (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gpd.h"
+
+namespace gpd {
+
+template <typename R> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+// Drone constants in the compute type, plus the float64 originals the FP32 path needs for its
+// cancellation-free rotor prologue (DESIGN.md "FP32 mode").
+template <typename R>
+struct DevDrone {
+    int model;
+    R M, L, ARM;            // ARM = L/sqrt(2)  (BaseAviary.py:847-848)
+    R KF, KM;
+    R J[3], JINV[3];
+    R GRAVITY, MAX_RPM;
+    R GND_EFF_COEFF, PROP_RADIUS, GND_EFF_H_CLIP;
+    R ROTOR[4][3];
+    R DRAG[3];
+    R DW1, DW2, DW3;
+    double KF_d, KM_d, GRAVITY_d, L_d, ARM_d, HOVER_RPM_d, MAX_RPM_d;
+};
+
+template <typename R>
+struct DevPid {
+    R P_FOR[3], I_FOR[3], D_FOR[3], P_TOR[3], I_TOR[3], D_TOR[3];
+    R PWM2RPM_SCALE, PWM2RPM_CONST, MIN_PWM, MAX_PWM;
+    R MIXER[4][3];
+    R GRAVITY, KF4;         // KF4 = 4*KF of the controller's own model (DSLPIDControl.py:198)
+};
+
+// Persistent per-drone state, SoA of 16-byte vectors (D = E*N drones):
+//   sP = (pos.x, pos.y, pos.z, rates.x)   sQ = quat xyzw   sV = (vel.x, vel.y, vel.z, rates.y)   sWz = rates.z
+//   aux_av = (ang_v.xyz, 0), aux_rpm = last_clipped_action   (outputs kept so gpd_get_state is exact)
+//   pid[k*D + d], k = 0..8
+template <typename R>
+struct SimPtrs {
+    typename Vec4<R>::type* sP;
+    typename Vec4<R>::type* sQ;
+    typename Vec4<R>::type* sV;
+    R* sWz;
+    typename Vec4<R>::type* aux_av;
+    typename Vec4<R>::type* aux_rpm;
+    R* pid;
+    int32_t* counter;       // [E] BaseAviary.step_counter
+    float* ep_ret;          // [E] running episode return (auto_reset only)
+    int32_t* ep_len;        // [E]
+    double* stat_slots;     // [grid][8] per-block statistics partials
+    const typename Vec4<R>::type* init_pos;   // [N] or [D]  (xyz, 0)
+    const typename Vec4<R>::type* init_quat;  // [N] or [D]
+    const typename Vec4<R>::type* target;     // [N] (xyz, 0)
+};
+
+template <typename R>
+struct StepArgs {
+    int64_t D;              // total drones
+    int64_t E;
+    int N, S, A, B, W;
+    int DPB, EPB;           // drones / envs per block
+    int env_kind, action_type, phy, auto_reset, init_per_env;
+    R dt, ctrl_dt, speed_limit;
+    double pyb_freq, episode_len;
+    SimPtrs<R> p;
+    const void* actions;
+    const float* obs_prev;
+    void* obs_out;
+    R* reward;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    float* terminal_kin;
+    const uint8_t* reset_mask;   // reset kernel only
+    DevDrone<R> drone;
+    DevPid<R> pid;
+};
+
+struct LaunchCfg {
+    int threads;
+    int64_t grid;
+    size_t smem;
+};
+
+// implemented once per precision in gpd_f32.cu / gpd_f64.cu
+template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
+template <typename R> cudaError_t launch_reset(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
+template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, R* state20, R* rpy_rates, R* pid_state,
+                                                   int32_t* counter, cudaStream_t st);
+template <typename R> cudaError_t launch_set_state(const StepArgs<R>& a, const R* state20, const R* rpy_rates,
+                                                   const R* pid_state, const int32_t* counter, cudaStream_t st);
+template <typename R> cudaError_t launch_pid(const DevPid<R>& c, int64_t n, R dt, const R* cur_pos, const R* cur_quat,
+                                             const R* cur_vel, const R* target_pos, const R* target_rpy,
+                                             const R* target_vel, const R* target_rates, R* pid_state, R* rpm_out,
+                                             R* pos_e_out, R* yaw_e_out, cudaStream_t st);
+template <typename R> cudaError_t launch_ground_effect(const DevDrone<R>& d, int64_t n, const R* rpm, const R* pos,
+                                                       const R* quat, R* out, uint8_t* applied, cudaStream_t st);
+template <typename R> cudaError_t launch_drag(const DevDrone<R>& d, int64_t n, const R* rpm, const R* quat,
+                                              const R* vel, R* out, cudaStream_t st);
+template <typename R> cudaError_t launch_downwash(const DevDrone<R>& d, int64_t E, int N, const R* pos, R* out,
+                                                  cudaStream_t st);
+template <typename R> cudaError_t launch_rollout_pid(const StepArgs<R>& a, int n_steps, const R* waypoints, int n_wp,
+                                                     int32_t* wp_counters, R* action, cudaStream_t st);
+template <typename R> cudaError_t launch_stats_reduce(const double* slots, int64_t nslots, double* out8,
+                                                      cudaStream_t st);
+
+size_t step_smem_bytes(int precision, int env_kind, int N, int DPB, int EPB);
+
+}  // namespace gpd

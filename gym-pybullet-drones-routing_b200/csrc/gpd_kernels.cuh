@@ -1,0 +1,712 @@
+// gpd_kernels.cuh — the fused step kernel and its helpers, templated on the compute type.
+// Included by gpd_f32.cu (float, FMA on) and gpd_f64.cu (double, -fmad=false).
+//
+// One thread per drone; a block owns EPB whole envs (DPB = EPB*N consecutive drones), so the
+// per-env reductions (MultiHover reward/termination, downwash) stay inside shared memory.
+// The 13-float integrator state lives in registers across the whole PYB_STEPS_PER_CTRL loop.
+// Observation rows are contiguous per block tile: the kinematic part is staged in shared memory
+// and written with coalesced 16-byte stores; the action-history part is a shifted global->global
+// copy of the previous observation (the RL observation IS the action ring, BaseRLAviary.py:317-318).
+#pragma once
+
+#include "gpd_math.cuh"
+
+namespace gpd {
+
+template <typename R> using V4 = typename Vec4<R>::type;
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// ---- shared-memory layout -------------------------------------------------------------
+//   stage : RL envs float[DPB*12] (kin part of each obs row) | Ctrl env R[DPB*20] (state20 rows)
+//   MULTI : snap R[DPB*3], red R[DPB*2], redi int[DPB], envf int[EPB*2]
+//   stats : float[4] + int[4]
+template <typename R>
+struct Smem {
+    unsigned char* base;
+    int DPB, EPB;
+    bool ctrl, multi;
+    __device__ float* stage_f() const { return reinterpret_cast<float*>(base); }
+    __device__ R* stage_r() const { return reinterpret_cast<R*>(base); }
+    __device__ size_t stage_bytes() const { return ctrl ? size_t(DPB) * 20 * sizeof(R) : size_t(DPB) * 12 * sizeof(float); }
+    __device__ R* snap() const { return reinterpret_cast<R*>(base + ((stage_bytes() + 15) & ~size_t(15))); }
+    __device__ R* red() const { return snap() + (multi ? size_t(DPB) * 3 : 0); }
+    __device__ int* redi() const { return reinterpret_cast<int*>(red() + (multi ? size_t(DPB) * 2 : 0)); }
+    __device__ int* envf() const { return redi() + (multi ? DPB : 0); }
+    __device__ float* stat_f() const { return reinterpret_cast<float*>(envf() + (multi ? 2 * EPB : 0)); }
+    __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4); }
+};
+
+__device__ __forceinline__ int float_to_ordered(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i)
+{
+    return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+// History part of the observation tile: out[row][12 + c] = prev[row][12 + c + A] (c < A*(B-1)),
+// newest entry = this step's action (BaseRLAviary.py:187, deque(maxlen=B)).  shift = 0 for reset (ring survives).
+template <bool VEC>
+__device__ __forceinline__ void copy_history(const float* __restrict__ prev, float* __restrict__ out,
+                                             const float* __restrict__ act, int64_t row0, int rows, int W, int A, int B,
+                                             bool shift)
+{
+    const int t = threadIdx.x, T = blockDim.x;
+    if constexpr (VEC) {     // A == 4: rows are whole float4s, the shift is one float4
+        const int W4 = W >> 2;
+        const float4* prev4 = reinterpret_cast<const float4*>(prev);
+        const float4* act4 = reinterpret_cast<const float4*>(act);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        const int total = rows * B;
+        for (int idx = t; idx < total; idx += T) {
+            int row = idx / B, c = idx - row * B;
+            int64_t rbase = (row0 + row) * W4 + 3;
+            float4 v;
+            if (shift) {
+                if (c < B - 1) v = prev ? ldg_stream(prev4 + rbase + c + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                else v = __ldg(act4 + row0 + row);
+            } else {
+                v = prev ? ldg_stream(prev4 + rbase + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            out4[rbase + c] = v;
+        }
+    } else {
+        const int H = A * B, keep = A * (B - 1);
+        const int total = rows * H;
+        for (int idx = t; idx < total; idx += T) {
+            int row = idx / H, c = idx - row * H;
+            int64_t rbase = (row0 + row) * (int64_t)W + 12;
+            float v;
+            if (shift) {
+                if (c < keep) v = prev ? __ldg(prev + rbase + c + A) : 0.f;
+                else v = __ldg(act + (row0 + row) * A + (c - keep));
+            } else {
+                v = prev ? __ldg(prev + rbase + c) : 0.f;
+            }
+            out[rbase + c] = v;
+        }
+    }
+}
+
+// Kinematic part of the observation tile (12 floats per row) from the shared staging buffer.
+template <bool VEC>
+__device__ __forceinline__ void write_kin(const float* __restrict__ stage, float* __restrict__ out, int64_t row0, int rows, int W)
+{
+    const int t = threadIdx.x, T = blockDim.x;
+    if constexpr (VEC) {
+        const int W4 = W >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(stage);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        for (int idx = t; idx < rows * 3; idx += T) {
+            int row = idx / 3, j = idx - row * 3;
+            out4[(row0 + row) * W4 + j] = s4[idx];
+        }
+    } else {
+        for (int idx = t; idx < rows * 12; idx += T) {
+            int row = idx / 12, j = idx - row * 12;
+            out[(row0 + row) * (int64_t)W + j] = stage[idx];
+        }
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ void load_state(const SimPtrs<R>& p, int64_t d, State<R>& s)
+{
+    V4<R> a = p.sP[d], q = p.sQ[d], v = p.sV[d];
+    s.px = a.x; s.py = a.y; s.pz = a.z; s.wx = a.w;
+    s.qx = q.x; s.qy = q.y; s.qz = q.z; s.qw = q.w;
+    s.vx = v.x; s.vy = v.y; s.vz = v.z; s.wy = v.w;
+    s.wz = p.sWz[d];
+}
+
+template <typename R>
+__device__ __forceinline__ void store_state(const SimPtrs<R>& p, int64_t d, const State<R>& s)
+{
+    p.sP[d] = M<R>::make4(s.px, s.py, s.pz, s.wx);
+    p.sQ[d] = M<R>::make4(s.qx, s.qy, s.qz, s.qw);
+    p.sV[d] = M<R>::make4(s.vx, s.vy, s.vz, s.wy);
+    p.sWz[d] = s.wz;
+}
+
+template <typename R>
+__device__ __forceinline__ void init_state(const StepArgs<R>& a, int64_t d, int i, State<R>& s)
+{
+    int64_t k = a.init_per_env ? d : (int64_t)i;
+    V4<R> ip = a.p.init_pos[k], iq = a.p.init_quat[k];
+    s.px = ip.x; s.py = ip.y; s.pz = ip.z;
+    s.qx = iq.x; s.qy = iq.y; s.qz = iq.z; s.qw = iq.w;
+    s.vx = s.vy = s.vz = R(0);
+    s.wx = s.wy = s.wz = R(0);
+}
+
+// _preprocessAction for the PID-family action types (BaseRLAviary.py:193-235).
+template <typename R>
+__device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, const State<R>& s, const float* act, R rpm[4])
+{
+    R st[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st[k] = a.p.pid[(int64_t)k * a.D + d];
+    R tp[3], trpy[3] = { R(0), R(0), R(0) }, tv[3] = { R(0), R(0), R(0) }, tr[3] = { R(0), R(0), R(0) }, pe[3], ye;
+    if (a.action_type == GPD_ACT_PID) {
+        // BaseAviary._calculateNextStep (BaseAviary.py:1105-1147), step_size = 1
+        R dx = R(act[0]) - s.px, dy = R(act[1]) - s.py, dz = R(act[2]) - s.pz;
+        R dist = M<R>::sqrt(dx * dx + dy * dy + dz * dz);
+        if (dist <= R(1)) { tp[0] = R(act[0]); tp[1] = R(act[1]); tp[2] = R(act[2]); }
+        else { tp[0] = s.px + dx / dist * R(1); tp[1] = s.py + dy / dist * R(1); tp[2] = s.pz + dz / dist * R(1); }
+    } else if (a.action_type == GPD_ACT_VEL) {
+        // BaseRLAviary.py:208-223; the unit vector and the speed are float32 expressions in the reference
+        float n = sqrtf(act[0] * act[0] + act[1] * act[1] + act[2] * act[2]);
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+        if (n != 0.f) { u0 = act[0] / n; u1 = act[1] / n; u2 = act[2] / n; }
+        float sp = (float)a.speed_limit * fabsf(act[3]);
+        tv[0] = R(sp * u0); tv[1] = R(sp * u1); tv[2] = R(sp * u2);
+        tp[0] = s.px; tp[1] = s.py; tp[2] = s.pz;
+        R roll, pitch, yaw;
+        quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+        trpy[2] = yaw;
+    } else {  // GPD_ACT_ONE_D_PID, BaseRLAviary.py:226-235
+        tp[0] = s.px + R(0.1) * R(0); tp[1] = s.py + R(0.1) * R(0); tp[2] = s.pz + R(0.1) * R(act[0]);
+    }
+    pid_compute(a.pid, a.ctrl_dt, s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, tp, trpy, tv, tr, st, rpm, pe, ye);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.p.pid[(int64_t)k * a.D + d] = st[k];
+}
+
+// ============================================================================================
+// The fused step kernel: BaseAviary.step (BaseAviary.py:259-383).
+//   LEAN  : plain Physics.DYN with an RPM-type action (no controller, no force models)
+//   MULTI : N > 1 (per-env reductions / downwash need block-level exchange)
+//   VEC   : A == 4 (observation rows are float4-granular)
+// ============================================================================================
+template <typename R, bool LEAN, bool MULTI, bool VEC>
+__global__ void __launch_bounds__(256)
+step_kernel(const __grid_constant__ StepArgs<R> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const bool ctrl = a.env_kind == GPD_ENV_CTRL;
+    Smem<R> sm{ smem_raw, a.DPB, a.EPB, ctrl, MULTI };
+    const int t = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * a.DPB;
+    const int64_t d = row0 + t;
+    const bool active = t < a.DPB && d < a.D;
+    const int rows = (int)min((int64_t)a.DPB, a.D - row0);
+    const int le = MULTI ? t / a.N : t;          // local env
+    const int i = MULTI ? t - le * a.N : 0;      // drone index in env
+    const int64_t e = MULTI ? (int64_t)blockIdx.x * a.EPB + le : d;
+    const DevDrone<R>& P = a.drone;
+
+    if (a.auto_reset) {
+        if (t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
+        __syncthreads();
+    }
+
+    // ---- state and action loads first (their latency overlaps the history copy below) ----
+    State<R> s;
+    s.px = s.py = s.pz = s.qx = s.qy = s.qz = R(0); s.qw = R(1);
+    s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
+    double rpm[4] = { 0., 0., 0., 0. };
+    float act[4] = { 0.f, 0.f, 0.f, 0.f };
+    R rpm_prev[4] = { R(0), R(0), R(0), R(0) };
+    if (active) {
+        load_state(a.p, d, s);
+        if (a.action_type == GPD_ACT_CTRL_RPM) {                 // CtrlAviary.py:140
+            V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
+            rpm[0] = clip(v.x, R(0), P.MAX_RPM); rpm[1] = clip(v.y, R(0), P.MAX_RPM);
+            rpm[2] = clip(v.z, R(0), P.MAX_RPM); rpm[3] = clip(v.w, R(0), P.MAX_RPM);
+        } else {
+            const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
+            if constexpr (VEC) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(ap));
+                act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+            } else {
+                for (int k = 0; k < a.A; ++k) act[k] = __ldg(ap + k);
+            }
+        }
+        if constexpr (!LEAN) {
+            if (a.phy & GPD_PHY_DRAG) {
+                V4<R> v = a.p.aux_rpm[d];
+                rpm_prev[0] = v.x; rpm_prev[1] = v.y; rpm_prev[2] = v.z; rpm_prev[3] = v.w;
+            }
+        }
+    }
+
+    // ---- action history of the observation: independent of the physics, issue it now ----
+    if (!ctrl)
+        copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
+                          row0, rows, a.W, a.A, a.B, true);
+
+    // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238) ----
+    if (a.action_type == GPD_ACT_RPM) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rpm[k] = P.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[k]));   // :192, float32 inner ops
+    } else if (a.action_type == GPD_ACT_ONE_D_RPM) {
+        double v = P.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[0]));                             // :225
+        rpm[0] = rpm[1] = rpm[2] = rpm[3] = v;
+    }
+    if constexpr (!LEAN) {
+        if (a.action_type == GPD_ACT_PID || a.action_type == GPD_ACT_VEL || a.action_type == GPD_ACT_ONE_D_PID) {
+            if (active) {
+                R r4[4];
+                pid_action(a, d, s, act, r4);
+                rpm[0] = r4[0]; rpm[1] = r4[1]; rpm[2] = r4[2]; rpm[3] = r4[3];
+            }
+        }
+    }
+    Forcing<R> F;
+    make_forcing(P, rpm, F);
+    const R rpm_r[4] = { (R)rpm[0], (R)rpm[1], (R)rpm[2], (R)rpm[3] };
+
+    // ---- PYB_STEPS_PER_CTRL substeps (BaseAviary.py:343-372), state in registers ----
+    R avx = R(0), avy = R(0), avz = R(0);
+    for (int sub = 0; sub < a.S; ++sub) {
+        R m[9];
+        quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);                  // :836 (shared with the force models)
+        if constexpr (LEAN) {
+            dyn_substep<R>(P, a.dt, s, m, F, nullptr, nullptr, avx, avy, avz);
+        } else {
+            R gnd[4], fb[3] = { R(0), R(0), R(0) };
+            const R* pg = nullptr;
+            const R* pb = nullptr;
+            if (a.phy & GPD_PHY_GND) {
+                R roll, pitch, yaw;
+                quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);     // snapshot rpy, :346-347,518
+                if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
+            }
+            if (a.phy & GPD_PHY_DRAG) {                          // :359,366: rpm = last_clipped_action
+                R db[3];
+                drag_body(P, sub == 0 ? rpm_prev : rpm_r, m, s.vx, s.vy, s.vz, db);
+                fb[0] += db[0]; fb[1] += db[1]; fb[2] += db[2];
+                pb = fb;
+            }
+            if constexpr (MULTI) {
+                if (a.phy & GPD_PHY_DW) {                        // :362,367 against the substep-start snapshot
+                    R* snap = sm.snap();
+                    __syncthreads();
+                    if (t < a.DPB) { snap[3 * t] = s.px; snap[3 * t + 1] = s.py; snap[3 * t + 2] = s.pz; }
+                    __syncthreads();
+                    R dw = R(0);
+                    const R* env = snap + 3 * (le * a.N);
+                    if (active)
+                        for (int j = 0; j < a.N; ++j)
+                            dw += downwash_pair(P, s.px, s.py, s.pz, env[3 * j], env[3 * j + 1], env[3 * j + 2]);
+                    fb[2] += dw;
+                    pb = fb;
+                }
+            }
+            dyn_substep<R>(P, a.dt, s, m, F, pg, pb, avx, avy, avz);
+        }
+    }
+
+    // ---- _updateAndStoreKinematicInformation (BaseAviary.py:374,509-519) + outputs ----
+    R roll, pitch, yaw;
+    quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+
+    R rew = R(-1);                      // CtrlAviary.py:144-200: dummy reward/flags
+    int term = 0, trunc = 0;
+    int32_t cnt = 0;
+    if (!ctrl) {
+        V4<R> tg = a.p.target[i];
+        R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
+        R dist = M<R>::sqrt(ex * ex + ey * ey + ez * ez);
+        R d2 = dist * dist;
+        R v = R(2) - d2 * d2;           // HoverAviary.py:78 / MultiHoverAviary.py:87
+        R r_i = v > R(0) ? v : R(0);
+        const R lim = a.env_kind == GPD_ENV_HOVER ? R(1.5) : R(2.0);       // HoverAviary.py:111 / MultiHoverAviary.py:124
+        int tr_i = (M<R>::abs(s.px) > lim || M<R>::abs(s.py) > lim || s.pz > R(2.0) ||
+                    M<R>::abs(roll) > R(.4) || M<R>::abs(pitch) > R(.4)) ? 1 : 0;
+        if constexpr (MULTI) {
+            R* red = sm.red();
+            int* redi = sm.redi();
+            __syncthreads();
+            if (t < a.DPB) { red[2 * t] = active ? r_i : R(0); red[2 * t + 1] = active ? dist : R(0); redi[t] = active ? tr_i : 0; }
+            __syncthreads();
+            if (active && i == 0) {     // in-order sums over the env's drones (MultiHoverAviary.py:86-88,103-105)
+                R rs = R(0), ds = R(0);
+                int tr = 0;
+                for (int j = 0; j < a.N; ++j) { rs += red[2 * (t + j)]; ds += red[2 * (t + j) + 1]; tr |= redi[t + j]; }
+                rew = rs;
+                term = a.env_kind == GPD_ENV_HOVER ? (red[2 * t + 1] < R(.0001)) : (ds < R(.0001));
+                trunc = tr;
+            }
+        } else {
+            rew = r_i; term = dist < R(.0001); trunc = tr_i;
+        }
+    }
+    if (active && i == 0) {
+        cnt = a.p.counter[e];
+        if (!ctrl && ((double)cnt / a.pyb_freq > a.episode_len)) trunc = 1;   // HoverAviary.py:114, counter BEFORE the increment
+        if (a.reward) a.reward[e] = rew;
+        if (a.terminated) a.terminated[e] = (uint8_t)term;
+        if (a.truncated) a.truncated[e] = (uint8_t)trunc;
+    }
+    int done = 0;
+    if (a.auto_reset) {
+        done = term | trunc;
+        if constexpr (MULTI) {
+            int* envf = sm.envf();
+            __syncthreads();
+            if (active && i == 0) envf[le] = done;
+            __syncthreads();
+            done = active ? envf[le] : 0;
+        }
+    }
+
+    float kin[12];
+    kin[0] = (float)s.px; kin[1] = (float)s.py; kin[2] = (float)s.pz;
+    kin[3] = (float)roll; kin[4] = (float)pitch; kin[5] = (float)yaw;
+    kin[6] = (float)s.vx; kin[7] = (float)s.vy; kin[8] = (float)s.vz;
+    kin[9] = (float)avx; kin[10] = (float)avy; kin[11] = (float)avz;
+    R out_rpm[4] = { rpm_r[0], rpm_r[1], rpm_r[2], rpm_r[3] };
+
+    if (a.auto_reset && active) {
+        if (i == 0) {                   // Monitor-style episode statistics
+            float er = a.p.ep_ret[e] + (float)rew;
+            int el = a.p.ep_len[e] + 1;
+            if (done) {
+                atomicAdd(&sm.stat_f()[0], er);
+                atomicAdd(&sm.stat_f()[1], er * er);
+                atomicAdd(&sm.stat_i()[0], 1);
+                atomicAdd(&sm.stat_i()[1], el);
+                atomicMin(&sm.stat_i()[2], float_to_ordered(er));
+                atomicMax(&sm.stat_i()[3], float_to_ordered(er));
+                if (term) atomicAdd(&sm.stat_f()[2], 1.f);
+                er = 0.f; el = 0;
+            }
+            a.p.ep_ret[e] = er;
+            a.p.ep_len[e] = el;
+        }
+        if (done) {
+            if (a.terminal_kin && !ctrl) {
+                float4* tk = reinterpret_cast<float4*>(a.terminal_kin) + d * 3;
+                tk[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
+                tk[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
+                tk[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+            }
+            init_state(a, d, i, s);     // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
+            quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+            avx = avy = avz = R(0);
+            out_rpm[0] = out_rpm[1] = out_rpm[2] = out_rpm[3] = R(0);       // last_clipped_action zeroed, :468
+            kin[0] = (float)s.px; kin[1] = (float)s.py; kin[2] = (float)s.pz;
+            kin[3] = (float)roll; kin[4] = (float)pitch; kin[5] = (float)yaw;
+#pragma unroll
+            for (int k = 6; k < 12; ++k) kin[k] = 0.f;
+        }
+    }
+    if (active) {
+        if (i == 0) a.p.counter[e] = (a.auto_reset && done) ? 0 : cnt + a.S;   // BaseAviary.py:382
+        store_state(a.p, d, s);
+        a.p.aux_av[d] = M<R>::make4(avx, avy, avz, R(0));
+        a.p.aux_rpm[d] = M<R>::make4(out_rpm[0], out_rpm[1], out_rpm[2], out_rpm[3]);
+    }
+
+    // ---- observation tile ----
+    if (ctrl) {                         // CtrlAviary.py:117: obs = state20 rows, contiguous for the whole tile
+        R* st = sm.stage_r();
+        if (t < a.DPB) {
+            R* r = st + 20 * t;
+            r[0] = s.px; r[1] = s.py; r[2] = s.pz; r[3] = s.qx; r[4] = s.qy; r[5] = s.qz; r[6] = s.qw;
+            r[7] = roll; r[8] = pitch; r[9] = yaw; r[10] = s.vx; r[11] = s.vy; r[12] = s.vz;
+            r[13] = avx; r[14] = avy; r[15] = avz; r[16] = out_rpm[0]; r[17] = out_rpm[1]; r[18] = out_rpm[2]; r[19] = out_rpm[3];
+        }
+        __syncthreads();
+        R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
+        for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
+    } else {
+        float* st = sm.stage_f();
+        if (t < a.DPB) {
+            float4* r = reinterpret_cast<float4*>(st) + 3 * t;
+            r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
+            r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
+            r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+        }
+        __syncthreads();
+        write_kin<VEC>(st, reinterpret_cast<float*>(a.obs_out), row0, rows, a.W);
+    }
+
+    if (a.auto_reset && t == 0) {       // fold this block's partial statistics into its own slot (no global atomics)
+        double* slot = a.p.stat_slots + (int64_t)blockIdx.x * 8;
+        int n = sm.stat_i()[0];
+        if (n > 0) {
+            slot[0] += (double)n;
+            slot[1] += (double)sm.stat_f()[0];
+            slot[2] += (double)sm.stat_i()[1];
+            slot[3] += (double)sm.stat_f()[1];
+            double mn = (double)ordered_to_float(sm.stat_i()[2]), mx = (double)ordered_to_float(sm.stat_i()[3]);
+            if (mn < slot[4]) slot[4] = mn;
+            if (mx > slot[5]) slot[5] = mx;
+            slot[7] += (double)sm.stat_f()[2];
+        }
+        slot[6] += (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)blockIdx.x * a.EPB) : rows);
+    }
+}
+
+// ============================================================================================
+// reset: BaseAviary.reset (BaseAviary.py:220-255) for the masked envs + observation of every env.
+// ============================================================================================
+template <typename R, bool VEC>
+__global__ void __launch_bounds__(256)
+reset_kernel(const __grid_constant__ StepArgs<R> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const bool ctrl = a.env_kind == GPD_ENV_CTRL;
+    Smem<R> sm{ smem_raw, a.DPB, a.EPB, ctrl, false };
+    const int t = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * a.DPB;
+    const int64_t d = row0 + t;
+    const bool active = t < a.DPB && d < a.D;
+    const int rows = (int)min((int64_t)a.DPB, a.D - row0);
+    const int le = t / a.N, i = t - le * a.N;
+    const int64_t e = (int64_t)blockIdx.x * a.EPB + le;
+
+    if (!ctrl && a.obs_out)
+        copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), nullptr, row0, rows, a.W, a.A, a.B, false);
+
+    State<R> s;
+    s.px = s.py = s.pz = s.qx = s.qy = s.qz = R(0); s.qw = R(1);
+    s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
+    R avx = R(0), avy = R(0), avz = R(0);
+    R rpm[4] = { R(0), R(0), R(0), R(0) };
+    if (active) {
+        bool doit = a.reset_mask == nullptr || a.reset_mask[e] != 0;
+        if (doit) {
+            init_state(a, d, i, s);
+            store_state(a.p, d, s);
+            a.p.aux_av[d] = M<R>::make4(R(0), R(0), R(0), R(0));
+            a.p.aux_rpm[d] = M<R>::make4(R(0), R(0), R(0), R(0));
+            if (i == 0) {
+                a.p.counter[e] = 0;
+                if (a.p.ep_ret) { a.p.ep_ret[e] = 0.f; a.p.ep_len[e] = 0; }
+            }
+        } else {
+            load_state(a.p, d, s);
+            V4<R> av = a.p.aux_av[d], rp = a.p.aux_rpm[d];
+            avx = av.x; avy = av.y; avz = av.z;
+            rpm[0] = rp.x; rpm[1] = rp.y; rpm[2] = rp.z; rpm[3] = rp.w;
+        }
+    }
+    if (!a.obs_out) return;
+    R roll, pitch, yaw;
+    quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+    if (ctrl) {
+        R* st = sm.stage_r();
+        if (t < a.DPB) {
+            R* r = st + 20 * t;
+            r[0] = s.px; r[1] = s.py; r[2] = s.pz; r[3] = s.qx; r[4] = s.qy; r[5] = s.qz; r[6] = s.qw;
+            r[7] = roll; r[8] = pitch; r[9] = yaw; r[10] = s.vx; r[11] = s.vy; r[12] = s.vz;
+            r[13] = avx; r[14] = avy; r[15] = avz; r[16] = rpm[0]; r[17] = rpm[1]; r[18] = rpm[2]; r[19] = rpm[3];
+        }
+        __syncthreads();
+        R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
+        for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
+    } else {
+        float* st = sm.stage_f();
+        if (t < a.DPB) {
+            float4* r = reinterpret_cast<float4*>(st) + 3 * t;
+            r[0] = make_float4((float)s.px, (float)s.py, (float)s.pz, (float)roll);
+            r[1] = make_float4((float)pitch, (float)yaw, (float)s.vx, (float)s.vy);
+            r[2] = make_float4((float)s.vz, (float)avx, (float)avy, (float)avz);
+        }
+        __syncthreads();
+        write_kin<VEC>(st, reinterpret_cast<float*>(a.obs_out), row0, rows, a.W);
+    }
+}
+
+// ---- state export / import (BaseAviary._getDroneStateVector, BaseAviary.py:541-561) ----
+template <typename R>
+__global__ void get_state_kernel(const StepArgs<R> a, R* __restrict__ state20, R* __restrict__ rpy_rates,
+                                 R* __restrict__ pid_state, int32_t* __restrict__ counter)
+{
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < a.E && counter) counter[d] = a.p.counter[d];
+    if (d >= a.D) return;
+    State<R> s;
+    load_state(a.p, d, s);
+    if (state20) {
+        R roll, pitch, yaw;
+        quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+        V4<R> av = a.p.aux_av[d], rp = a.p.aux_rpm[d];
+        R* r = state20 + d * 20;
+        r[0] = s.px; r[1] = s.py; r[2] = s.pz; r[3] = s.qx; r[4] = s.qy; r[5] = s.qz; r[6] = s.qw;
+        r[7] = roll; r[8] = pitch; r[9] = yaw; r[10] = s.vx; r[11] = s.vy; r[12] = s.vz;
+        r[13] = av.x; r[14] = av.y; r[15] = av.z; r[16] = rp.x; r[17] = rp.y; r[18] = rp.z; r[19] = rp.w;
+    }
+    if (rpy_rates) { rpy_rates[d * 3] = s.wx; rpy_rates[d * 3 + 1] = s.wy; rpy_rates[d * 3 + 2] = s.wz; }
+    if (pid_state && a.p.pid)
+        for (int k = 0; k < 9; ++k) pid_state[d * 9 + k] = a.p.pid[(int64_t)k * a.D + d];
+}
+
+template <typename R>
+__global__ void set_state_kernel(const StepArgs<R> a, const R* __restrict__ state20, const R* __restrict__ rpy_rates,
+                                 const R* __restrict__ pid_state, const int32_t* __restrict__ counter)
+{
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < a.E && counter) a.p.counter[d] = counter[d];
+    if (d >= a.D) return;
+    State<R> s;
+    load_state(a.p, d, s);
+    if (state20) {
+        const R* r = state20 + d * 20;
+        s.px = r[0]; s.py = r[1]; s.pz = r[2]; s.qx = r[3]; s.qy = r[4]; s.qz = r[5]; s.qw = r[6];
+        s.vx = r[10]; s.vy = r[11]; s.vz = r[12];
+        a.p.aux_av[d] = M<R>::make4(r[13], r[14], r[15], R(0));
+        a.p.aux_rpm[d] = M<R>::make4(r[16], r[17], r[18], r[19]);
+    }
+    if (rpy_rates) { s.wx = rpy_rates[d * 3]; s.wy = rpy_rates[d * 3 + 1]; s.wz = rpy_rates[d * 3 + 2]; }
+    store_state(a.p, d, s);
+    if (pid_state && a.p.pid)
+        for (int k = 0; k < 9; ++k) a.p.pid[(int64_t)k * a.D + d] = pid_state[d * 9 + k];
+}
+
+// ---- batched DSLPIDControl.computeControl (control/DSLPIDControl.py:82-145) ----
+template <typename R>
+__global__ void pid_kernel(const DevPid<R> c, int64_t n, R dt, const R* __restrict__ cur_pos, const R* __restrict__ cur_quat,
+                           const R* __restrict__ cur_vel, const R* __restrict__ target_pos, const R* __restrict__ target_rpy,
+                           const R* __restrict__ target_vel, const R* __restrict__ target_rates, R* __restrict__ pid_state,
+                           R* __restrict__ rpm_out, R* __restrict__ pos_e_out, R* __restrict__ yaw_e_out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    R tp[3], trpy[3] = { 0, 0, 0 }, tv[3] = { 0, 0, 0 }, tr[3] = { 0, 0, 0 }, st[9], rpm[4], pe[3], ye;
+    for (int j = 0; j < 3; ++j) {
+        tp[j] = target_pos[k * 3 + j];
+        if (target_rpy) trpy[j] = target_rpy[k * 3 + j];
+        if (target_vel) tv[j] = target_vel[k * 3 + j];
+        if (target_rates) tr[j] = target_rates[k * 3 + j];
+    }
+    for (int j = 0; j < 9; ++j) st[j] = pid_state[k * 9 + j];
+    pid_compute(c, dt, cur_pos[k * 3], cur_pos[k * 3 + 1], cur_pos[k * 3 + 2], cur_quat[k * 4], cur_quat[k * 4 + 1],
+                cur_quat[k * 4 + 2], cur_quat[k * 4 + 3], cur_vel[k * 3], cur_vel[k * 3 + 1], cur_vel[k * 3 + 2],
+                tp, trpy, tv, tr, st, rpm, pe, ye);
+    for (int j = 0; j < 9; ++j) pid_state[k * 9 + j] = st[j];
+    for (int j = 0; j < 4; ++j) rpm_out[k * 4 + j] = rpm[j];
+    if (pos_e_out) for (int j = 0; j < 3; ++j) pos_e_out[k * 3 + j] = pe[j];
+    if (yaw_e_out) yaw_e_out[k] = ye;
+}
+
+// ---- force-model unit-test kernels (BaseAviary.py:715-811) ----
+template <typename R>
+__global__ void ground_effect_kernel(const DevDrone<R> P, int64_t n, const R* __restrict__ rpm, const R* __restrict__ pos,
+                                     const R* __restrict__ quat, R* __restrict__ out, uint8_t* __restrict__ applied)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    R m[9], roll, pitch, yaw, g[4];
+    const R* q = quat + k * 4;
+    quat_to_mat(q[0], q[1], q[2], q[3], m);
+    quat_to_euler(q[0], q[1], q[2], q[3], roll, pitch, yaw);
+    R r4[4] = { rpm[k * 4], rpm[k * 4 + 1], rpm[k * 4 + 2], rpm[k * 4 + 3] };
+    bool ok = ground_effect(P, r4, pos[k * 3 + 2], m, roll, pitch, g);
+    for (int j = 0; j < 4; ++j) out[k * 4 + j] = g[j];
+    if (applied) applied[k] = ok ? 1 : 0;
+}
+
+template <typename R>
+__global__ void drag_kernel(const DevDrone<R> P, int64_t n, const R* __restrict__ rpm, const R* __restrict__ quat,
+                            const R* __restrict__ vel, R* __restrict__ out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    R m[9], o[3];
+    const R* q = quat + k * 4;
+    quat_to_mat(q[0], q[1], q[2], q[3], m);
+    R r4[4] = { rpm[k * 4], rpm[k * 4 + 1], rpm[k * 4 + 2], rpm[k * 4 + 3] };
+    drag_body(P, r4, m, vel[k * 3], vel[k * 3 + 1], vel[k * 3 + 2], o);
+    for (int j = 0; j < 3; ++j) out[k * 3 + j] = o[j];
+}
+
+template <typename R>
+__global__ void downwash_kernel(const DevDrone<R> P, int64_t E, int N, const R* __restrict__ pos, R* __restrict__ out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= E * N) return;
+    int64_t e = k / N;
+    const R* env = pos + e * N * 3;
+    const R* me = pos + k * 3;
+    R dw = R(0);
+    for (int j = 0; j < N; ++j) dw += downwash_pair(P, me[0], me[1], me[2], env[3 * j], env[3 * j + 1], env[3 * j + 2]);
+    out[k] = dw;
+}
+
+// ============================================================================================
+// examples/pid.py:127-147 as one launch: n_steps x { step(action); action = DSLPID(obs, waypoint) }.
+// Ctrl env, one thread per drone, state + controller state in registers for the whole rollout.
+// ============================================================================================
+template <typename R>
+__global__ void __launch_bounds__(128)
+rollout_pid_kernel(const __grid_constant__ StepArgs<R> a, int n_steps, const R* __restrict__ waypoints, int n_wp,
+                   int32_t* __restrict__ wp_counters, R* __restrict__ action)
+{
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= a.D) return;
+    const int i = (int)(d % a.N);
+    const int64_t e = d / a.N;
+    const DevDrone<R>& P = a.drone;
+    State<R> s;
+    load_state(a.p, d, s);
+    R st[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st[k] = a.p.pid[(int64_t)k * a.D + d];
+    V4<R> av4 = reinterpret_cast<V4<R>*>(action)[d];
+    R act[4] = { av4.x, av4.y, av4.z, av4.w };
+    V4<R> rp = a.p.aux_rpm[d];
+    R rpm_prev[4] = { rp.x, rp.y, rp.z, rp.w };
+    int wp = wp_counters[d];
+    const int64_t ik = a.init_per_env ? d : (int64_t)i;
+    V4<R> ip = a.p.init_pos[ik], iq = a.p.init_quat[ik];
+    R ir, ipt, iy;
+    quat_to_euler(iq.x, iq.y, iq.z, iq.w, ir, ipt, iy);
+    const R trpy[3] = { ir, ipt, iy }, zero3[3] = { R(0), R(0), R(0) };
+    R avx = a.p.aux_av[d].x, avy = a.p.aux_av[d].y, avz = a.p.aux_av[d].z;
+    R rpm_r[4] = { rpm_prev[0], rpm_prev[1], rpm_prev[2], rpm_prev[3] };
+    for (int it = 0; it < n_steps; ++it) {
+        double rpm[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rpm_r[k] = clip(act[k], R(0), P.MAX_RPM); rpm[k] = rpm_r[k]; }   // CtrlAviary.py:140
+        Forcing<R> F;
+        make_forcing(P, rpm, F);
+        for (int sub = 0; sub < a.S; ++sub) {
+            R m[9];
+            quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);
+            R gnd[4], fb[3] = { R(0), R(0), R(0) };
+            const R* pg = nullptr;
+            const R* pb = nullptr;
+            if (a.phy & GPD_PHY_GND) {
+                R roll, pitch, yaw;
+                quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+                if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
+            }
+            if (a.phy & GPD_PHY_DRAG) {
+                drag_body(P, sub == 0 ? rpm_prev : rpm_r, m, s.vx, s.vy, s.vz, fb);
+                pb = fb;
+            }
+            dyn_substep<R>(P, a.dt, s, m, F, pg, pb, avx, avy, avz);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rpm_prev[k] = rpm_r[k];
+        // examples/pid.py:142-147 computeControlFromState(state=obs[j], target_pos=[wp.xy, INIT z], target_rpy=INIT_RPYS[j])
+        const R tp[3] = { waypoints[3 * wp], waypoints[3 * wp + 1], ip.z };
+        R pe[3], ye;
+        pid_compute(a.pid, a.ctrl_dt, s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, tp, trpy, zero3, zero3,
+                    st, act, pe, ye);
+        wp = wp < n_wp - 1 ? wp + 1 : 0;                                                   // examples/pid.py:151
+    }
+    store_state(a.p, d, s);
+    a.p.aux_av[d] = M<R>::make4(avx, avy, avz, R(0));
+    a.p.aux_rpm[d] = M<R>::make4(rpm_r[0], rpm_r[1], rpm_r[2], rpm_r[3]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.p.pid[(int64_t)k * a.D + d] = st[k];
+    reinterpret_cast<V4<R>*>(action)[d] = M<R>::make4(act[0], act[1], act[2], act[3]);
+    wp_counters[d] = wp;
+    if (i == 0) a.p.counter[e] += a.S * n_steps;
+}
+
+}  // namespace gpd

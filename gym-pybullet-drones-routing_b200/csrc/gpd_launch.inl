@@ -1,0 +1,105 @@
+// gpd_launch.inl — launchers, compiled once per precision with GPD_REAL defined (gpd_f32.cu / gpd_f64.cu).
+#include "gpd_kernels.cuh"
+
+namespace gpd {
+
+using Real = GPD_REAL;
+
+template <bool LEAN, bool MULTI, bool VEC>
+static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
+{
+    step_kernel<Real, LEAN, MULTI, VEC><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
+{
+    const bool rpm_like = a.action_type == GPD_ACT_RPM || a.action_type == GPD_ACT_ONE_D_RPM ||
+                          a.action_type == GPD_ACT_CTRL_RPM;
+    const bool lean = rpm_like && a.phy == 0;
+    const bool multi = a.N > 1;
+    const bool vec = a.A == 4 && a.env_kind != GPD_ENV_CTRL && (a.W % 4 == 0);
+    const int key = (lean ? 4 : 0) | (multi ? 2 : 0) | (vec ? 1 : 0);
+    switch (key) {
+    case 0: return launch_step_t<false, false, false>(a, lc, st);
+    case 1: return launch_step_t<false, false, true>(a, lc, st);
+    case 2: return launch_step_t<false, true, false>(a, lc, st);
+    case 3: return launch_step_t<false, true, true>(a, lc, st);
+    case 4: return launch_step_t<true, false, false>(a, lc, st);
+    case 5: return launch_step_t<true, false, true>(a, lc, st);
+    case 6: return launch_step_t<true, true, false>(a, lc, st);
+    default: return launch_step_t<true, true, true>(a, lc, st);
+    }
+}
+
+template <>
+cudaError_t launch_reset<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
+{
+    const bool vec = a.A == 4 && a.env_kind != GPD_ENV_CTRL && (a.W % 4 == 0);
+    if (vec) reset_kernel<Real, true><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
+    else reset_kernel<Real, false><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <>
+cudaError_t launch_get_state<Real>(const StepArgs<Real>& a, Real* state20, Real* rpy_rates, Real* pid_state,
+                                   int32_t* counter, cudaStream_t st)
+{
+    get_state_kernel<Real><<<blocks_for(a.D, 128), 128, 0, st>>>(a, state20, rpy_rates, pid_state, counter);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_set_state<Real>(const StepArgs<Real>& a, const Real* state20, const Real* rpy_rates,
+                                   const Real* pid_state, const int32_t* counter, cudaStream_t st)
+{
+    set_state_kernel<Real><<<blocks_for(a.D, 128), 128, 0, st>>>(a, state20, rpy_rates, pid_state, counter);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_pid<Real>(const DevPid<Real>& c, int64_t n, Real dt, const Real* cur_pos, const Real* cur_quat,
+                             const Real* cur_vel, const Real* target_pos, const Real* target_rpy, const Real* target_vel,
+                             const Real* target_rates, Real* pid_state, Real* rpm_out, Real* pos_e_out, Real* yaw_e_out,
+                             cudaStream_t st)
+{
+    pid_kernel<Real><<<blocks_for(n, 128), 128, 0, st>>>(c, n, dt, cur_pos, cur_quat, cur_vel, target_pos, target_rpy,
+                                                         target_vel, target_rates, pid_state, rpm_out, pos_e_out, yaw_e_out);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_ground_effect<Real>(const DevDrone<Real>& d, int64_t n, const Real* rpm, const Real* pos,
+                                       const Real* quat, Real* out, uint8_t* applied, cudaStream_t st)
+{
+    ground_effect_kernel<Real><<<blocks_for(n, 128), 128, 0, st>>>(d, n, rpm, pos, quat, out, applied);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_drag<Real>(const DevDrone<Real>& d, int64_t n, const Real* rpm, const Real* quat, const Real* vel,
+                              Real* out, cudaStream_t st)
+{
+    drag_kernel<Real><<<blocks_for(n, 128), 128, 0, st>>>(d, n, rpm, quat, vel, out);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_downwash<Real>(const DevDrone<Real>& d, int64_t E, int N, const Real* pos, Real* out, cudaStream_t st)
+{
+    downwash_kernel<Real><<<blocks_for(E * N, 128), 128, 0, st>>>(d, E, N, pos, out);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_rollout_pid<Real>(const StepArgs<Real>& a, int n_steps, const Real* waypoints, int n_wp,
+                                     int32_t* wp_counters, Real* action, cudaStream_t st)
+{
+    rollout_pid_kernel<Real><<<blocks_for(a.D, 128), 128, 0, st>>>(a, n_steps, waypoints, n_wp, wp_counters, action);
+    return cudaGetLastError();
+}
+
+}  // namespace gpd

@@ -1,0 +1,3 @@
+from .CtrlAviary import CtrlAviary  # noqa: F401
+from .HoverAviary import HoverAviary  # noqa: F401
+from .MultiHoverAviary import MultiHoverAviary  # noqa: F401

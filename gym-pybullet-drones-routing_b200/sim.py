@@ -1,0 +1,210 @@
+"""``BatchedSim`` — thin host wrapper of one ``gpd_sim`` handle (``include/gpd.h``).
+
+PyTorch is used only for device memory and streams: every I/O buffer is a caller-visible
+CUDA tensor handed to the C ABI as a raw pointer (zero-copy).  The observation is kept in a
+ping-pong pair because the RL observation carries the action ring (reference
+``BaseRLAviary.py:317-318``): step k reads the history from the buffer step k-1 wrote.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .params import DroneParams, PIDParams, default_pid_params
+from .utils.enums import DroneModel
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedSim:
+    def __init__(self, drone: DroneParams, num_envs: int, num_drones: int = 1, env_kind: str = "hover",
+                 action_type: str = "rpm", pyb_freq: int = 240, ctrl_freq: int = 30, physics_flags: int = 0,
+                 precision: str = "f32", device: int = 0, auto_reset: bool = False, pid: PIDParams | None = None,
+                 target_pos=None, episode_len_sec: float = 8.0, init_xyz=None, init_rpy=None,
+                 threads_per_block: int = 0):
+        self.lib = _lib.load()
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        if pyb_freq % ctrl_freq != 0:
+            raise ValueError('[ERROR] in BaseAviary.__init__(), pyb_freq is not divisible by env_freq.')
+        self.E, self.N = int(num_envs), int(num_drones)
+        self.env_kind, self.action_type = env_kind, action_type
+        self.is_ctrl = env_kind == "ctrl"
+        self.precision = precision
+        self.real = torch.float64 if precision == "f64" else torch.float32
+        self.np_real = np.float64 if precision == "f64" else np.float32
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.auto_reset = bool(auto_reset)
+        cfg = _lib.ConfigC()
+        cfg.device = self.device_index
+        cfg.precision = _lib.GPD_F64 if precision == "f64" else _lib.GPD_F32
+        cfg.num_envs, cfg.num_drones = self.E, self.N
+        cfg.pyb_freq, cfg.ctrl_freq = int(pyb_freq), int(ctrl_freq)
+        cfg.env_kind = _lib.ENV_CODES[env_kind]
+        cfg.action_type = _lib.ACT_CODES[action_type]
+        cfg.physics_flags = int(physics_flags)
+        cfg.auto_reset = int(self.auto_reset)
+        cfg.threads_per_block = int(threads_per_block)
+        cfg.episode_len_sec = float(episode_len_sec)
+        cfg.speed_limit = 0.03 * drone.MAX_SPEED_KMH * (1000 / 3600)       # BaseRLAviary.py:95
+        cfg.drone = _lib.drone_params_c(drone)
+        if pid is None and drone.model in (DroneModel.CF2X, DroneModel.CF2P):
+            # in-env controllers are CF2X even for a CF2P env (BaseRLAviary.py:75-76); the pid.py-style rollout
+            # passes the drone's own model explicitly
+            pid = default_pid_params(DroneModel.CF2X)
+        if pid is not None:
+            cfg.pid = _lib.pid_params_c(pid)
+        self._target = None
+        if target_pos is not None:
+            self._target = np.ascontiguousarray(np.asarray(target_pos, dtype=np.float64).reshape(self.N, 3))
+            cfg.target_pos = self._target.ctypes.data_as(C.POINTER(C.c_double))
+        h = C.c_void_p()
+        _lib.check(self.lib.gpd_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.A = self.lib.gpd_action_width(h)
+        self.W = self.lib.gpd_obs_width(h)
+        self.S = self.lib.gpd_substeps(h)
+        self.B = 0 if self.is_ctrl else ctrl_freq // 2
+        self.act_dtype = self.real if self.is_ctrl else torch.float32
+        self.obs_dtype = self.real if self.is_ctrl else torch.float32
+        with torch.cuda.device(self.device):
+            self.obs_buf = [torch.zeros((self.E, self.N, self.W), dtype=self.obs_dtype, device=self.device)
+                            for _ in range(2)]
+            self.reward = torch.zeros(self.E, dtype=self.real, device=self.device)
+            self.terminated = torch.zeros(self.E, dtype=torch.uint8, device=self.device)
+            self.truncated = torch.zeros(self.E, dtype=torch.uint8, device=self.device)
+            self.terminal_kin = (torch.zeros((self.E, self.N, 12), dtype=torch.float32, device=self.device)
+                                 if self.auto_reset and not self.is_ctrl else None)
+        self._cur = 0
+        self._have_prev = False
+        if init_xyz is not None or init_rpy is not None:
+            self.set_init_poses(init_xyz, init_rpy)
+            self.reset()
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_init_poses(self, xyz, rpy):
+        """initial_xyzs / initial_rpys (BaseAviary.py:194-207): (N,3) for all envs or (E,N,3) per env."""
+        xyz = np.asarray(xyz, dtype=np.float64)
+        rpy = np.zeros_like(xyz) if rpy is None else np.asarray(rpy, dtype=np.float64)
+        per_env = xyz.ndim == 3
+        shape = (self.E, self.N, 3) if per_env else (self.N, 3)
+        if xyz.shape != shape or rpy.shape != shape:
+            raise ValueError(f"initial poses must have shape {shape}")
+        xyz, rpy = np.ascontiguousarray(xyz), np.ascontiguousarray(rpy)
+        dp = C.POINTER(C.c_double)
+        _lib.check(self.lib.gpd_set_init_poses(self.h, xyz.ctypes.data_as(dp), rpy.ctypes.data_as(dp), int(per_env)))
+
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """BaseAviary.reset for the masked envs (None = all); returns the observation of every env."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        nxt = self._cur ^ 1
+        prev = self.obs_buf[self._cur] if self._have_prev else None
+        _lib.check(self.lib.gpd_reset(self.h, _ptr(mask), _ptr(prev), _ptr(self.obs_buf[nxt]), self._stream()))
+        self._cur, self._have_prev = nxt, True
+        return self.obs_buf[nxt]
+
+    def step(self, actions: torch.Tensor):
+        """One BaseAviary.step on device tensors.  Returns views of internal buffers: the observation stays
+        valid until the step after next (ping-pong); reward/terminated/truncated until the next step."""
+        if actions.dtype != self.act_dtype or not actions.is_cuda or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=self.act_dtype).contiguous()
+        if actions.numel() != self.E * self.N * self.A:
+            raise ValueError(f"actions must have {self.E}x{self.N}x{self.A} elements, got {tuple(actions.shape)}")
+        nxt = self._cur ^ 1
+        prev = self.obs_buf[self._cur] if self._have_prev else None
+        _lib.check(self.lib.gpd_step(self.h, _ptr(actions), _ptr(prev), _ptr(self.obs_buf[nxt]), _ptr(self.reward),
+                                     _ptr(self.terminated), _ptr(self.truncated), _ptr(self.terminal_kin),
+                                     self._stream()))
+        self._cur, self._have_prev = nxt, True
+        return self.obs_buf[nxt], self.reward, self.terminated, self.truncated
+
+    # host-buffer path: what a numpy call site (the reference's own step signature) sees
+    def step_host(self, actions: np.ndarray, out=None):
+        adt = self.np_real if self.is_ctrl else np.float32
+        a = np.ascontiguousarray(actions, dtype=adt)
+        if a.size != self.E * self.N * self.A:
+            raise ValueError(f"actions must have {self.E}x{self.N}x{self.A} elements, got {a.shape}")
+        if out is None:
+            out = self.alloc_host_outputs()
+        obs, rew, term, trunc, tkin = out
+        _lib.check(self.lib.gpd_step_host(self.h, C.c_void_p(a.ctypes.data), C.c_void_p(obs.ctypes.data),
+                                          C.c_void_p(rew.ctypes.data), C.c_void_p(term.ctypes.data),
+                                          C.c_void_p(trunc.ctypes.data),
+                                          None if tkin is None else C.c_void_p(tkin.ctypes.data), self._stream()))
+        return out
+
+    def reset_host(self, mask: np.ndarray | None = None, obs: np.ndarray | None = None):
+        if obs is None:
+            obs = np.empty((self.E, self.N, self.W), dtype=self.np_real if self.is_ctrl else np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        _lib.check(self.lib.gpd_reset_host(self.h, None if m is None else C.c_void_p(m.ctypes.data),
+                                           C.c_void_p(obs.ctypes.data), self._stream()))
+        return obs
+
+    def alloc_host_outputs(self, pinned: bool = False):
+        odt = self.np_real if self.is_ctrl else np.float32
+        shapes = [((self.E, self.N, self.W), odt), ((self.E,), self.np_real), ((self.E,), np.uint8), ((self.E,), np.uint8)]
+        if pinned:
+            arrs = [torch.empty(s, dtype=torch.from_numpy(np.empty(0, d)).dtype).pin_memory().numpy() for s, d in shapes]
+        else:
+            arrs = [np.empty(s, dtype=d) for s, d in shapes]
+        tkin = None
+        if self.auto_reset and not self.is_ctrl:
+            tkin = (torch.empty((self.E, self.N, 12), dtype=torch.float32).pin_memory().numpy() if pinned
+                    else np.empty((self.E, self.N, 12), np.float32))
+        return (*arrs, tkin)
+
+    # ------------------------------------------------------------------
+    def get_state(self):
+        """state20 (E,N,20), rpy_rates (E,N,3), pid_state (E,N,9), step_counter (E,) — BaseAviary.py:541-561."""
+        st = torch.empty((self.E, self.N, 20), dtype=self.real, device=self.device)
+        rr = torch.empty((self.E, self.N, 3), dtype=self.real, device=self.device)
+        ps = torch.empty((self.E, self.N, 9), dtype=self.real, device=self.device)
+        cnt = torch.empty(self.E, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.gpd_get_state(self.h, _ptr(st), _ptr(rr), _ptr(ps), _ptr(cnt), self._stream()))
+        return st, rr, ps, cnt
+
+    def set_state(self, state20=None, rpy_rates=None, pid_state=None, step_counter=None):
+        def prep(t, dt):
+            return None if t is None else t.to(device=self.device, dtype=dt).contiguous()
+        st, rr, ps = prep(state20, self.real), prep(rpy_rates, self.real), prep(pid_state, self.real)
+        cnt = prep(step_counter, torch.int32)
+        _lib.check(self.lib.gpd_set_state(self.h, _ptr(st), _ptr(rr), _ptr(ps), _ptr(cnt), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()   # the temporaries above must outlive the kernel
+
+    def rollout_pid(self, n_ctrl_steps: int, waypoints: torch.Tensor, wp_counters: torch.Tensor, action: torch.Tensor):
+        """examples/pid.py:127-147 loop in one launch (Ctrl env); updates wp_counters and action in place."""
+        assert waypoints.dtype == self.real and action.dtype == self.real and wp_counters.dtype == torch.int32
+        assert waypoints.is_cuda and action.is_cuda and wp_counters.is_cuda
+        _lib.check(self.lib.gpd_rollout_pid(self.h, int(n_ctrl_steps), _ptr(waypoints.contiguous()),
+                                            int(waypoints.shape[0]), _ptr(wp_counters), _ptr(action), self._stream()))
+
+    def episode_stats(self, clear: bool = False) -> np.ndarray:
+        out = (C.c_double * 8)()
+        _lib.check(self.lib.gpd_episode_stats(self.h, out, int(clear), self._stream()))
+        return np.array(list(out))
+
+    @property
+    def obs(self) -> torch.Tensor:
+        return self.obs_buf[self._cur]
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.gpd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,376 @@
+"""-m gpu: the CUDA path (through the C ABI, include/gpd.h) against the golden vectors generated from the
+reference and against the CPU oracle on seeded inputs.  FP64: <= 1e-9 relative over up to 1,000 ctrl steps
+(action replay); FP32: <= 1e-4 relative on position/velocity over 100 ctrl steps (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from helpers import (S_ANGV, S_POS, S_QUAT, S_RATES, S_RPM, S_RPY, S_VEL, angle_err, case_setup, load_golden,
+                     make_oracle, quat_err, rel_err, traj_cases)
+from gpd_b200.params import default_pid_params, load_drone_params
+from gpd_b200.utils.enums import DroneModel
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = {"traj_hovervel_cf2p_48.npz": 1e-6}     # float32 BLAS sdot inside the reference's VEL mapping
+
+
+def make_sim(kw, num_envs=1, precision="f64", auto_reset=False, tpb=0):
+    from gpd_b200.sim import BatchedSim
+    dp = load_drone_params(kw["model"])
+    n = kw["num_drones"]
+    target = None
+    if kw["env_kind"] == "hover":
+        target = np.array([[0., 0., 1.]])
+    elif kw["env_kind"] == "multihover":
+        init = np.stack([np.array([x * 4 * dp.L for x in range(n)]), np.array([y * 4 * dp.L for y in range(n)]),
+                         np.ones(n) * (dp.COLLISION_H / 2 - dp.COLLISION_Z_OFFSET + .1)], axis=1)
+        target = init + np.array([[0, 0, 1 / (i + 1)] for i in range(n)])
+    return BatchedSim(dp, num_envs, n, env_kind=kw["env_kind"], action_type=kw["action_type"], pyb_freq=kw["pyb_freq"],
+                      ctrl_freq=kw["ctrl_freq"], physics_flags=kw["physics_flags"], precision=precision,
+                      auto_reset=auto_reset, target_pos=target, init_xyz=kw["init_xyz"], init_rpy=kw["init_rpy"],
+                      threads_per_block=tpb)
+
+
+def state_np(sim):
+    st, rr, ps, cnt = sim.get_state()
+    return (np.concatenate([st.double().cpu().numpy(), rr.double().cpu().numpy()], axis=-1), ps.double().cpu().numpy(),
+            cnt.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", traj_cases())
+def test_cuda_f64_replays_reference_trajectory(name):
+    g = load_golden(name)
+    kw = case_setup(g)
+    E = 3                                             # same actions in 3 envs: exercises the batch axis + block tail
+    sim = make_sim(kw, num_envs=E)
+    tol = TOL64.get(name, 1e-9)
+    acts = g["actions"]
+    ck = {int(t): i for i, t in enumerate(g["ckpt_idx"])}
+    osteps = {int(t): i for i, t in enumerate(g["obs_steps"])}
+    obs = sim.reset()
+    assert np.max(np.abs(obs.double().cpu().numpy()[1] - g["obs0"])) <= 1e-7 * (tol / 1e-9)
+    adt = torch.float64 if kw["env_kind"] == "ctrl" else torch.float32
+    dev_acts = torch.as_tensor(np.repeat(acts[:, None], E, axis=1), dtype=adt).cuda()
+    for t in range(acts.shape[0]):
+        obs, rew, term, trunc = sim.step(dev_acts[t])
+        if t in ck:
+            i = ck[t]
+            ref = g["ckpt_state"][i]
+            st_all, _, cnt = state_np(sim)
+            for e in (0, E - 1):
+                st = st_all[e]
+                assert rel_err(st[:, S_POS], ref[:, S_POS]) <= tol, (t, "pos")
+                assert rel_err(st[:, S_VEL], ref[:, S_VEL]) <= tol, (t, "vel")
+                assert rel_err(st[:, S_RATES], ref[:, S_RATES]) <= tol, (t, "rpy_rates")
+                assert rel_err(st[:, S_ANGV], ref[:, S_ANGV]) <= tol, (t, "ang_v")
+                assert quat_err(st[:, S_QUAT], ref[:, S_QUAT]) <= tol, (t, "quat")
+                assert angle_err(st[:, S_RPY], ref[:, S_RPY]) <= tol * 10, (t, "rpy")
+                assert rel_err(st[:, S_RPM], ref[:, S_RPM]) <= tol, (t, "rpm")
+            r = rew.cpu().numpy()
+            assert np.all(np.abs(r - g["ckpt_reward"][i]) <= tol * max(abs(g["ckpt_reward"][i]), 1e-3) * 10), (t, "reward")
+            assert np.all(term.cpu().numpy().astype(bool) == bool(g["ckpt_terminated"][i])), (t, "terminated")
+            assert np.all(trunc.cpu().numpy().astype(bool) == bool(g["ckpt_truncated"][i])), (t, "truncated")
+            assert np.all(cnt == g["ckpt_counter"][i])
+        if t in osteps:
+            want = g["obs_rows"][osteps[t]]
+            got = obs.double().cpu().numpy()
+            scale = np.maximum(np.abs(want), 1.0)
+            for e in (0, E - 1):
+                assert np.max(np.abs(got[e] - want) / scale) <= max(1e-9, tol * 100), (t, "obs")
+    sim.close()
+
+
+def _random_init(rng, E, N):
+    xyz = rng.uniform([-1, -1, 0.2], [1, 1, 1.5], size=(E, N, 3))
+    rpy = rng.uniform(-0.2, 0.2, size=(E, N, 3))
+    return xyz, rpy
+
+
+@pytest.mark.parametrize("model,env_kind,N,freq,flags,steps", [
+    (DroneModel.CF2X, "hover", 1, 30, 0, 1000),
+    (DroneModel.CF2P, "hover", 1, 48, 0, 300),
+    (DroneModel.CF2X, "multihover", 2, 30, 3, 300),      # BASELINE config 3 shape: DYN+GND+DRAG, FP64
+    (DroneModel.RACE, "multihover", 3, 30, 0, 200),
+])
+def test_cuda_f64_vs_oracle_random_inits(model, env_kind, N, freq, flags, steps):
+    """1,000-step action replay from randomised per-env initial poses, E=257 (not a multiple of the block)."""
+    rng = np.random.default_rng(7)
+    E = 257
+    xyz, rpy = _random_init(rng, E, N)
+    if N > 1:
+        xyz[..., 2] = rng.uniform(0.03, 0.4, size=(E, N))           # near the ground: ground effect active
+    kw = dict(model=model, env_kind=env_kind, action_type="rpm", num_drones=N, pyb_freq=240, ctrl_freq=freq,
+              physics_flags=flags, init_xyz=xyz, init_rpy=rpy)
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E)
+    sim.reset()
+    scale = 0.05 if env_kind == "hover" else 0.3
+    for t in range(steps):
+        a = (scale * rng.standard_normal(size=(E, N, 4))).astype(np.float32)
+        obs, rew, term, trunc = sim.step(torch.from_numpy(a).cuda())
+        o_ref, r_ref, te_ref, tr_ref = ref.step(a, nthreads=4)
+        if t % 50 == 49 or t == steps - 1:
+            st, _, cnt = state_np(sim)
+            rs = np.concatenate([ref.state20, ref.rpy_rates], axis=-1)
+            for sl, nm in ((S_POS, "pos"), (S_VEL, "vel"), (S_RATES, "rates"), (S_ANGV, "ang_v")):
+                assert rel_err(st[..., sl], rs[..., sl]) <= 1e-9, (t, nm)
+            assert quat_err(st[..., S_QUAT], rs[..., S_QUAT]) <= 1e-9
+            assert np.array_equal(cnt, ref.step_counter)
+            assert np.max(np.abs(rew.cpu().numpy() - r_ref) / np.maximum(np.abs(r_ref), 1e-3)) <= 1e-8
+            assert np.array_equal(term.cpu().numpy(), te_ref) and np.array_equal(trunc.cpu().numpy(), tr_ref)
+            assert np.max(np.abs(obs.cpu().numpy().astype(np.float64) - o_ref) / np.maximum(np.abs(o_ref), 1.0)) <= 1e-6
+    sim.close()
+
+
+@pytest.mark.parametrize("model,env_kind,N,freq,scale", [
+    (DroneModel.CF2X, "hover", 1, 30, 0.05), (DroneModel.CF2X, "hover", 1, 30, 1.0),
+    (DroneModel.CF2P, "hover", 1, 48, 0.05), (DroneModel.CF2X, "multihover", 2, 30, 1.0),
+    (DroneModel.RACE, "hover", 1, 30, 0.3),
+])
+def test_cuda_f32_within_1e4_over_100_steps(model, env_kind, N, freq, scale):
+    """FP32 throughput mode: <= 1e-4 relative on position and velocity over 100 ctrl steps vs the FP64 oracle.
+    Error metric: ||dx||_2 / max(||x_ref||_2, 1e-3) per drone."""
+    rng = np.random.default_rng(11)
+    E = 512
+    kw = dict(model=model, env_kind=env_kind, action_type="rpm", num_drones=N, pyb_freq=240, ctrl_freq=freq,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E, precision="f32")
+    sim.reset()
+    worst = {"pos": 0.0, "vel": 0.0}
+    for t in range(100):
+        a = rng.uniform(-scale, scale, size=(E, N, 4)).astype(np.float32)
+        sim.step(torch.from_numpy(a).cuda())
+        ref.step(a, nthreads=4)
+        if t % 10 == 9:
+            st, _, _ = state_np(sim)
+            worst["pos"] = max(worst["pos"], rel_err(st[..., S_POS], ref.state20[..., S_POS]))
+            worst["vel"] = max(worst["vel"], rel_err(st[..., S_VEL], ref.state20[..., S_VEL]))
+    assert worst["pos"] <= 1e-4 and worst["vel"] <= 1e-4, worst
+    sim.close()
+
+
+@pytest.mark.parametrize("model", ["cf2x", "cf2p"])
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-12), ("f32", 2e-4)])
+def test_cuda_pid_teacher_forced(model, precision, tol):
+    """Batched DSLPIDControl.computeControl against the reference's call log, identical inputs each call."""
+    from gpd_b200.control.DSLPIDControl import DSLPIDControl
+    g = load_golden(f"pid_calls_{model}.npz")
+    ins, outs, sa = g["inputs"], g["outputs"], g["state_after"]
+    c = DSLPIDControl(DroneModel(model), num=2, precision=precision)
+    rdt = torch.float64 if precision == "f64" else torch.float32
+    for t in range(ins.shape[0]):
+        if t == int(g["reset_at"]):
+            c.reset()
+        # teacher forcing: controller state from the reference before the call
+        prev = np.zeros(9) if t in (0, int(g["reset_at"])) else sa[t - 1]
+        c.state[:] = torch.as_tensor(prev, dtype=rdt).cuda()
+        x = ins[t]
+        rpm, pos_e, yaw_e = c.computeControl(float(g["dt"]), x[0:3], x[3:7], x[7:10], np.zeros(3), x[10:13], x[13:16],
+                                             x[16:19], x[19:22])
+        rpm, pos_e, yaw_e = rpm.double().cpu().numpy(), pos_e.double().cpu().numpy(), yaw_e.double().cpu().numpy()
+        for row in (0, 1):
+            assert rel_err(rpm[row], outs[t, 0:4]) <= tol, (t, rpm[row], outs[t, 0:4])
+            assert np.max(np.abs(pos_e[row] - outs[t, 4:7])) <= (1e-15 if precision == "f64" else 1e-6)
+            assert abs(((yaw_e[row] - outs[t, 7]) + np.pi) % (2 * np.pi) - np.pi) <= (1e-12 if precision == "f64" else 1e-5)
+        st = c.state.double().cpu().numpy()[0]
+        np.testing.assert_allclose(st, sa[t], rtol=1e-12 if precision == "f64" else 1e-4,
+                                   atol=1e-13 if precision == "f64" else 1e-5)
+
+
+@pytest.mark.parametrize("model", ["cf2x", "cf2p", "racer"])
+def test_cuda_force_models(model):
+    """gpd_force_* against the recorded applyExternalForce arguments of the reference (<= 1e-12 relative)."""
+    import ctypes as C
+    from gpd_b200 import _lib
+    L = _lib.load()
+    g = load_golden("forces.npz")
+    d = _lib.drone_params_c(load_drone_params(DroneModel(model)))
+    inp = g[model + "_inputs"]
+    T, N = inp.shape[0], inp.shape[1]
+    flat = torch.as_tensor(inp.reshape(T * N, 17)).cuda()
+    pos, quat, vel, rpm = (flat[:, 0:3].contiguous(), flat[:, 3:7].contiguous(), flat[:, 10:13].contiguous(),
+                           flat[:, 13:17].contiguous())
+    p = lambda t: C.c_void_p(t.data_ptr())
+    ge = torch.empty((T * N, 4), dtype=torch.float64, device="cuda")
+    ok = torch.empty((T * N,), dtype=torch.uint8, device="cuda")
+    _lib.check(L.gpd_force_ground_effect(0, 1, C.byref(d), T * N, p(rpm), p(pos), p(quat), p(ge), p(ok), None))
+    dr = torch.empty((T * N, 3), dtype=torch.float64, device="cuda")
+    _lib.check(L.gpd_force_drag(0, 1, C.byref(d), T * N, p(rpm), p(quat), p(vel), p(dr), None))
+    dw = torch.empty((T, N), dtype=torch.float64, device="cuda")
+    posT = pos.reshape(T, N, 3).contiguous()
+    _lib.check(L.gpd_force_downwash(0, 1, C.byref(d), T, N, p(posT), p(dw), None))
+    torch.cuda.synchronize()
+    assert rel_err(ge.cpu().numpy(), g[model + "_gnd"].reshape(T * N, 4), floor=1e-12) <= 1e-12
+    assert np.array_equal(ok.cpu().numpy(), g[model + "_gnd_applied"].reshape(-1))
+    assert rel_err(dr.cpu().numpy(), g[model + "_drag_body"].reshape(T * N, 3), floor=1e-12) <= 1e-12
+    want = g[model + "_dw"]
+    assert np.max(np.abs(dw.cpu().numpy() - want) / np.maximum(np.abs(want), 1e-12)) <= 1e-11
+
+
+def test_cuda_reset_quirks_and_env_api():
+    """Ring survives reset (BaseRLAviary.py:153-154); truncation clock (BaseAviary.py:379-382); env façade API."""
+    from gpd_b200.envs import HoverAviary
+    g = load_golden("reset_quirks.npz")
+    env = HoverAviary(num_envs=2, precision="f64")
+    assert env.observation_space.shape == (1, 72) and env.action_space.shape == (1, 4)
+    assert env.ACTION_BUFFER_SIZE == 15 and env.PYB_STEPS_PER_CTRL == 8 and env.EPISODE_LEN_SEC == 8
+    acts = torch.as_tensor(g["actions"]).float().cuda()
+    env.reset()
+    for t in range(int(g["reset_after"])):
+        env.step(acts[t].expand(2, 1, 4).contiguous())
+    rows = [env.reset()[0][1].double().cpu().numpy()]
+    for t in range(int(g["reset_after"]), acts.shape[0]):
+        rows.append(env.step(acts[t].expand(2, 1, 4).contiguous())[0][1].double().cpu().numpy())
+    np.testing.assert_allclose(np.array(rows), g["obs_after_reset_then_steps"], rtol=1e-7, atol=1e-9)
+    env.close()
+    for freq in (30, 48):
+        env = HoverAviary(num_envs=1, ctrl_freq=freq, precision="f64")
+        env.reset()
+        first = None
+        z = torch.zeros((1, 1, 4), dtype=torch.float32, device="cuda")
+        for t in range(400):
+            _, _, te, tr, info = env.step(z)
+            if bool(tr[0]) and first is None:
+                first = t
+        assert first == int(g[f"first_truncated_step_{freq}"]) == {30: 241, 48: 385}[freq]
+        assert info == {"answer": 42}
+        env.close()
+    with pytest.raises(ValueError):
+        HoverAviary(pyb_freq=240, ctrl_freq=7)
+
+
+def test_cuda_auto_reset_terminal_obs_and_stats():
+    """SB3-style auto-reset inside the kernel: done envs restart from the initial pose, the terminal kinematic
+    observation is kept, Monitor-style episode statistics agree with a host-side recount (oracle-driven)."""
+    rng = np.random.default_rng(3)
+    E = 300
+    kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    sim = make_sim(kw, num_envs=E, precision="f64", auto_reset=True)
+    ref = make_oracle(kw, num_envs=E)
+    sim.reset()
+    ep_ret = np.zeros(E); ep_len = np.zeros(E, int)
+    n_ep = 0; sum_ret = 0.0; sum_len = 0; n_term = 0; rmin, rmax = np.inf, -np.inf
+    for t in range(60):
+        a = rng.uniform(-1, 1, size=(E, 1, 4)).astype(np.float32)
+        obs, rew, term, trunc = sim.step(torch.from_numpy(a).cuda())
+        o_ref, r_ref, te_ref, tr_ref = ref.step(a)
+        o_ref = o_ref.copy()
+        done = (te_ref | tr_ref).astype(bool)
+        assert np.array_equal((term | trunc).cpu().numpy().astype(bool), done)
+        tk = sim.terminal_kin.cpu().numpy()
+        assert np.max(np.abs(tk[done][:, 0] - o_ref[done][:, 0, :12])) <= 1e-6 if done.any() else True
+        ep_ret += r_ref; ep_len += 1
+        for e in np.nonzero(done)[0]:
+            n_ep += 1; sum_ret += ep_ret[e]; sum_len += ep_len[e]; n_term += int(te_ref[e])
+            rmin, rmax = min(rmin, ep_ret[e]), max(rmax, ep_ret[e])
+            ep_ret[e] = 0; ep_len[e] = 0
+        if done.any():
+            o_reset = ref.reset(done.astype(np.uint8))
+            o_ref[done] = o_reset[done]
+        assert np.max(np.abs(obs.cpu().numpy() - o_ref)) <= 1e-6
+    stats = sim.episode_stats()
+    assert stats[0] == n_ep and n_ep > 0
+    assert abs(stats[1] - sum_ret) <= 1e-4 * max(1.0, abs(sum_ret))
+    assert stats[2] == sum_len and stats[6] == 60 * E and stats[7] == n_term
+    assert abs(stats[4] - rmin) <= 1e-5 * max(1, abs(rmin)) and abs(stats[5] - rmax) <= 1e-5 * max(1, abs(rmax))
+    sim.close()
+
+
+def test_cuda_get_set_state_roundtrip_and_host_path():
+    """gpd_get_state/gpd_set_state checkpoint a run bit-exactly; gpd_step_host equals gpd_step."""
+    rng = np.random.default_rng(5)
+    E = 130
+    kw = dict(model=DroneModel.CF2P, env_kind="hover", action_type="pid", num_drones=1, pyb_freq=240, ctrl_freq=48,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    a = rng.uniform(-1, 1, size=(12, E, 1, 3)).astype(np.float32)
+    s1 = make_sim(kw, num_envs=E)
+    s1.reset()
+    for t in range(6):
+        s1.step(torch.from_numpy(a[t]).cuda())
+    st, rr, ps, cnt = s1.get_state()
+    s2 = make_sim(kw, num_envs=E)
+    s2.set_state(st, rr, ps, cnt)
+    s2.reset(torch.zeros(E, dtype=torch.uint8))            # no env reset: only primes obs with a zero ring
+    for t in range(6, 12):
+        o1, r1, _, _ = s1.step(torch.from_numpy(a[t]).cuda())
+        o2, r2, _, _ = s2.step(torch.from_numpy(a[t]).cuda())
+    x1, x2 = s1.get_state(), s2.get_state()
+    for u, v in zip(x1, x2):
+        assert torch.equal(u, v)
+    assert torch.equal(o1[..., :12], o2[..., :12]) and torch.equal(r1, r2)
+    # host path
+    s3 = make_sim(kw, num_envs=E)
+    s4 = make_sim(kw, num_envs=E)
+    s3.reset(); s4.reset_host()
+    for t in range(5):
+        od, rd, td, trd = s3.step(torch.from_numpy(a[t]).cuda())
+        oh, rh, th, trh, _ = s4.step_host(a[t])
+    assert np.array_equal(od.cpu().numpy(), oh) and np.array_equal(rd.cpu().numpy(), rh)
+    assert np.array_equal(td.cpu().numpy(), th) and np.array_equal(trd.cpu().numpy(), trh)
+    for s in (s1, s2, s3, s4):
+        s.close()
+
+
+def test_cuda_rollout_pid_matches_stepwise_loop():
+    """gpd_rollout_pid (examples/pid.py loop in one launch) == gpd_step + gpd_pid_compute called step by step,
+    and both track the oracle over a short horizon (closed loop is chaotic beyond ~20 steps, SURVEY finding 6)."""
+    from gpd_b200.control.DSLPIDControl import DSLPIDControl
+    from oracle import oracle as orc
+    E, N, steps = 70, 2, 16
+    model = DroneModel.CF2P
+    dp = load_drone_params(model)
+    rng = np.random.default_rng(9)
+    xyz = rng.uniform([-.3, -.3, 0.1], [.3, .3, 0.6], size=(E, N, 3))
+    rpy = np.zeros((E, N, 3)); rpy[..., 2] = rng.uniform(-.5, .5, size=(E, N))
+    kw = dict(model=model, env_kind="ctrl", action_type="ctrl_rpm", num_drones=N, pyb_freq=240, ctrl_freq=48,
+              physics_flags=0, init_xyz=xyz, init_rpy=rpy)
+    n_wp = 48
+    wps = np.stack([.3 * np.cos(np.arange(n_wp) / n_wp * 2 * np.pi), .3 * np.sin(np.arange(n_wp) / n_wp * 2 * np.pi),
+                    np.zeros(n_wp)], axis=1)
+    from gpd_b200.sim import BatchedSim
+    def mk():
+        return BatchedSim(dp, E, N, env_kind="ctrl", action_type="ctrl_rpm", pyb_freq=240, ctrl_freq=48,
+                          precision="f64", pid=default_pid_params(model), init_xyz=xyz, init_rpy=rpy)
+    # (a) one launch
+    sa = mk()
+    wp_a = torch.as_tensor(rng.integers(0, n_wp, size=(E, N)), dtype=torch.int32).cuda()
+    wp0 = wp_a.clone()
+    act_a = torch.zeros((E, N, 4), dtype=torch.float64, device="cuda")
+    sa.rollout_pid(steps, torch.as_tensor(wps).cuda(), wp_a, act_a)
+    # (b) stepwise through the public pieces
+    sb = mk()
+    ctrl = DSLPIDControl(model, num=E * N, precision="f64")
+    act_b = torch.zeros((E, N, 4), dtype=torch.float64, device="cuda")
+    wp_b = wp0.clone().long()
+    wps_t = torch.as_tensor(wps).cuda()
+    init_z = torch.as_tensor(xyz[..., 2]).cuda()
+    trpy = torch.as_tensor(rpy).cuda().reshape(-1, 3)
+    # (c) oracle
+    ref = make_oracle(kw, num_envs=E)
+    pid_o = orc.make_pid(default_pid_params(model))
+    pst = np.zeros((E, N, 9)); act_o = np.zeros((E, N, 4)); wp_o = wp0.cpu().numpy().copy()
+    for t in range(steps):
+        obs, _, _, _ = sb.step(act_b)
+        tp = torch.cat([wps_t[wp_b.reshape(-1)][:, 0:2], init_z.reshape(-1, 1)], dim=1)
+        rpm, _, _ = ctrl.computeControlFromState(1 / 48, obs.reshape(-1, 20), tp, trpy)
+        act_b = rpm.reshape(E, N, 4).clone()
+        wp_b = torch.where(wp_b < n_wp - 1, wp_b + 1, torch.zeros_like(wp_b))
+        ref.step(act_o)
+        for e in range(E):
+            for i in range(N):
+                s = ref.state20[e, i]
+                r, _, _ = orc.pid_compute(pid_o, 1 / 48, s[0:3], s[3:7], s[10:13],
+                                          [wps[wp_o[e, i], 0], wps[wp_o[e, i], 1], xyz[e, i, 2]], rpy[e, i], None, None, pst[e, i])
+                act_o[e, i] = r
+        wp_o = np.where(wp_o < n_wp - 1, wp_o + 1, 0)
+    xa, xb = sa.get_state(), sb.get_state()
+    assert torch.equal(wp_a.long(), wp_b)
+    assert rel_err(xa[0][..., 0:3].cpu().numpy(), xb[0][..., 0:3].cpu().numpy()) <= 1e-12
+    assert rel_err(act_a.cpu().numpy(), act_b.cpu().numpy()) <= 1e-10
+    assert rel_err(xa[0][..., 0:3].cpu().numpy(), ref.state20[..., 0:3]) <= 1e-7
+    assert rel_err(act_a.cpu().numpy(), act_o) <= 1e-6
+    sa.close(); sb.close()
