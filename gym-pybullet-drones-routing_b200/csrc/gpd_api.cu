@@ -40,6 +40,7 @@ struct gpd_sim {
     int A, B, W, S;
     int64_t D;
     LaunchCfg lc;
+    int dpb = 0;
     std::vector<void*> allocs;
     StepArgs<float> a32;
     StepArgs<double> a64;
@@ -79,6 +80,7 @@ static void fill_drone(const gpd_drone_params& p, DevDrone<R>& d)
     d.DW1 = (R)p.DW_COEFF_1; d.DW2 = (R)p.DW_COEFF_2; d.DW3 = (R)p.DW_COEFF_3;
     d.KF_d = p.KF; d.KM_d = p.KM; d.GRAVITY_d = p.GRAVITY; d.L_d = p.L; d.ARM_d = p.L / std::sqrt(2.0);
     d.HOVER_RPM_d = p.HOVER_RPM; d.MAX_RPM_d = p.MAX_RPM;
+    d.DT_INV_M = (R)0; d.DT_JINV[0] = d.DT_JINV[1] = d.DT_JINV[2] = (R)0;
 }
 
 template <typename R>
@@ -163,6 +165,8 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.dt = (R)(1.0 / c.pyb_freq); a.ctrl_dt = (R)(1.0 / c.ctrl_freq); a.speed_limit = (R)c.speed_limit;
     a.pyb_freq = (double)c.pyb_freq; a.episode_len = c.episode_len_sec;
     fill_drone(c.drone, a.drone);
+    a.drone.DT_INV_M = (R)((1.0 / c.pyb_freq) / c.drone.M);
+    for (int k = 0; k < 3; ++k) a.drone.DT_JINV[k] = (R)((1.0 / c.pyb_freq) * c.drone.J_INV[k]);
     fill_pid(c.pid, a.pid);
     int rc;
     V *sP, *sQ, *sV, *av, *rp; R* wz;
@@ -200,7 +204,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     if ((rc = dev_alloc(s, &dt_, (size_t)c.num_drones, false))) return rc;
     CU(cudaMemcpy(dt_, ht.data(), sizeof(V) * c.num_drones, cudaMemcpyHostToDevice));
     a.p.target = dt_;
-    a.DPB = s->lc.threads >= c.num_drones ? (s->lc.threads / c.num_drones) * c.num_drones : c.num_drones;
+    a.DPB = s->dpb;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207
     std::vector<double> xyz((size_t)c.num_drones * 3), rpy((size_t)c.num_drones * 3, 0.0);
@@ -268,8 +272,12 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     int N = cfg->num_drones;
     int DPB = T >= N ? (T / N) * N : N;
     if (DPB > T) T = (DPB + 31) / 32 * 32;
+    // single-drone RL envs: half of the block integrates, the other half streams the action history
+    const bool spec = N == 1 && !ctrl && T >= 64;
+    if (spec) DPB = T / 2;
     int EPB = DPB / N;
     s->lc.threads = T;
+    s->dpb = DPB;
     s->lc.grid = (cfg->num_envs + EPB - 1) / EPB;
     s->lc.smem = smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
     if (s->lc.grid > 0x7fffffffLL) { delete s; return fail(GPD_ERR_INVALID, "too many envs for one launch"); }

@@ -21,6 +21,7 @@ struct DevDrone {
     R KF, KM;
     R J[3], JINV[3];
     R GRAVITY, MAX_RPM;
+    R DT_INV_M, DT_JINV[3]; // FP32 mode: PYB_TIMESTEP/M and PYB_TIMESTEP*J^-1 (filled by gpd_create)
     R GND_EFF_COEFF, PROP_RADIUS, GND_EFF_H_CLIP;
     R ROTOR[4][3];
     R DRAG[3];

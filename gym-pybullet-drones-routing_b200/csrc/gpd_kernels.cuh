@@ -54,45 +54,74 @@ __device__ __forceinline__ float ordered_to_float(int i)
 }
 
 // History part of the observation tile: out[row][12 + c] = prev[row][12 + c + A] (c < A*(B-1)),
-// newest entry = this step's action (BaseRLAviary.py:187, deque(maxlen=B)).  shift = 0 for reset (ring survives).
+// newest entry = this step's action (BaseRLAviary.py:187, deque(maxlen=B)).  shift = false for reset (ring survives).
+// Executed by CT "copier" threads (index ct): either the whole block or, warp-specialised, its upper half.
+// Element k of the tile maps to (row, c) = (k / Hc, k % Hc); a thread visits k = ct, ct+CT, ... so (row, c) advances
+// by a fixed (CT / Hc, CT % Hc) with carry — no per-element division.
 template <bool VEC>
 __device__ __forceinline__ void copy_history(const float* __restrict__ prev, float* __restrict__ out,
                                              const float* __restrict__ act, int64_t row0, int rows, int W, int A, int B,
-                                             bool shift)
+                                             bool shift, int ct, int CT)
 {
-    const int t = threadIdx.x, T = blockDim.x;
+    constexpr int U = 8;     // independent loads in flight per thread before the first store (memory-level parallelism)
     if constexpr (VEC) {     // A == 4: rows are whole float4s, the shift is one float4
         const int W4 = W >> 2;
         const float4* prev4 = reinterpret_cast<const float4*>(prev);
         const float4* act4 = reinterpret_cast<const float4*>(act);
         float4* out4 = reinterpret_cast<float4*>(out);
         const int total = rows * B;
-        for (int idx = t; idx < total; idx += T) {
-            int row = idx / B, c = idx - row * B;
-            int64_t rbase = (row0 + row) * W4 + 3;
-            float4 v;
-            if (shift) {
-                if (c < B - 1) v = prev ? ldg_stream(prev4 + rbase + c + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                else v = __ldg(act4 + row0 + row);
-            } else {
-                v = prev ? ldg_stream(prev4 + rbase + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int qs = CT / B, rs = CT - qs * B;
+        int row = ct / B, c = ct - row * B;
+        for (int base = ct; base < total; base += U * CT) {
+            float4 v[U];
+            int64_t dst[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                dst[j] = -1;
+                if (base + j * CT < total) {
+                    int64_t rbase = (row0 + row) * W4 + 3;
+                    dst[j] = rbase + c;
+                    if (shift) {
+                        if (c < B - 1) v[j] = prev ? ldg_stream(prev4 + rbase + c + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        else v[j] = __ldg(act4 + row0 + row);
+                    } else {
+                        v[j] = prev ? ldg_stream(prev4 + rbase + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                c += rs; row += qs;
+                if (c >= B) { c -= B; row += 1; }
             }
-            out4[rbase + c] = v;
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (dst[j] >= 0) out4[dst[j]] = v[j];
         }
     } else {
         const int H = A * B, keep = A * (B - 1);
         const int total = rows * H;
-        for (int idx = t; idx < total; idx += T) {
-            int row = idx / H, c = idx - row * H;
-            int64_t rbase = (row0 + row) * (int64_t)W + 12;
-            float v;
-            if (shift) {
-                if (c < keep) v = prev ? __ldg(prev + rbase + c + A) : 0.f;
-                else v = __ldg(act + (row0 + row) * A + (c - keep));
-            } else {
-                v = prev ? __ldg(prev + rbase + c) : 0.f;
+        const int qs = CT / H, rs = CT - qs * H;
+        int row = ct / H, c = ct - row * H;
+        for (int base = ct; base < total; base += U * CT) {
+            float v[U];
+            int64_t dst[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                dst[j] = -1;
+                if (base + j * CT < total) {
+                    int64_t rbase = (row0 + row) * (int64_t)W + 12;
+                    dst[j] = rbase + c;
+                    if (shift) {
+                        if (c < keep) v[j] = prev ? __ldg(prev + rbase + c + A) : 0.f;
+                        else v[j] = __ldg(act + (row0 + row) * A + (c - keep));
+                    } else {
+                        v[j] = prev ? __ldg(prev + rbase + c) : 0.f;
+                    }
+                }
+                c += rs; row += qs;
+                if (c >= H) { c -= H; row += 1; }
             }
-            out[rbase + c] = v;
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (dst[j] >= 0) out[dst[j]] = v[j];
         }
     }
 }
@@ -203,12 +232,23 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     const int i = MULTI ? t - le * a.N : 0;      // drone index in env
     const int64_t e = MULTI ? (int64_t)blockIdx.x * a.EPB + le : d;
     const DevDrone<R>& P = a.drone;
+    // Warp specialisation (single-drone RL envs): threads [0, DPB) integrate the physics, threads [DPB, T) stream the
+    // action history; the two roles overlap instead of queueing behind each other in the same warps.
+    const bool spec = !MULTI && !ctrl && (int)blockDim.x >= 2 * a.DPB;
+    const bool run_physics = !spec || t < a.DPB;
 
     if (a.auto_reset) {
         if (t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
         __syncthreads();
     }
 
+    if (spec) {
+        if (t >= a.DPB)
+            copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
+                              row0, rows, a.W, a.A, a.B, true, t - a.DPB, (int)blockDim.x - a.DPB);
+    }
+
+    if (run_physics) {
     // ---- state and action loads first (their latency overlaps the history copy below) ----
     State<R> s;
     s.px = s.py = s.pz = s.qx = s.qy = s.qz = R(0); s.qw = R(1);
@@ -240,9 +280,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     }
 
     // ---- action history of the observation: independent of the physics, issue it now ----
-    if (!ctrl)
+    if (!ctrl && !spec)
         copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
-                          row0, rows, a.W, a.A, a.B, true);
+                          row0, rows, a.W, a.A, a.B, true, t, (int)blockDim.x);
 
     // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238) ----
     if (a.action_type == GPD_ACT_RPM) {
@@ -269,9 +309,10 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     R avx = R(0), avy = R(0), avz = R(0);
     for (int sub = 0; sub < a.S; ++sub) {
         R m[9];
-        quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);                  // :836 (shared with the force models)
+        const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);    // :836 (shared with the force models)
+        const bool last = sub == a.S - 1;
         if constexpr (LEAN) {
-            dyn_substep<R>(P, a.dt, s, m, F, nullptr, nullptr, avx, avy, avz);
+            dyn_substep<R>(P, a.dt, s, m, omz, F, nullptr, nullptr, last, avx, avy, avz);
         } else {
             R gnd[4], fb[3] = { R(0), R(0), R(0) };
             const R* pg = nullptr;
@@ -302,7 +343,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
                     pb = fb;
                 }
             }
-            dyn_substep<R>(P, a.dt, s, m, F, pg, pb, avx, avy, avz);
+            dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, last, avx, avy, avz);
         }
     }
 
@@ -408,28 +449,30 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
         a.p.aux_rpm[d] = M<R>::make4(out_rpm[0], out_rpm[1], out_rpm[2], out_rpm[3]);
     }
 
-    // ---- observation tile ----
-    if (ctrl) {                         // CtrlAviary.py:117: obs = state20 rows, contiguous for the whole tile
-        R* st = sm.stage_r();
-        if (t < a.DPB) {
-            R* r = st + 20 * t;
+    // ---- stage this drone's observation row in shared memory ----
+    if (t < a.DPB) {
+        if (ctrl) {                     // CtrlAviary.py:117: obs = state20 rows
+            R* r = sm.stage_r() + 20 * t;
             r[0] = s.px; r[1] = s.py; r[2] = s.pz; r[3] = s.qx; r[4] = s.qy; r[5] = s.qz; r[6] = s.qw;
             r[7] = roll; r[8] = pitch; r[9] = yaw; r[10] = s.vx; r[11] = s.vy; r[12] = s.vz;
             r[13] = avx; r[14] = avy; r[15] = avz; r[16] = out_rpm[0]; r[17] = out_rpm[1]; r[18] = out_rpm[2]; r[19] = out_rpm[3];
-        }
-        __syncthreads();
-        R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
-        for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
-    } else {
-        float* st = sm.stage_f();
-        if (t < a.DPB) {
-            float4* r = reinterpret_cast<float4*>(st) + 3 * t;
+        } else {
+            float4* r = reinterpret_cast<float4*>(sm.stage_f()) + 3 * t;
             r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
             r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
             r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
         }
-        __syncthreads();
-        write_kin<VEC>(st, reinterpret_cast<float*>(a.obs_out), row0, rows, a.W);
+    }
+    }   // run_physics
+
+    // ---- observation tile: coalesced write of the staged rows by the whole block ----
+    __syncthreads();
+    if (ctrl) {                         // the tile's state20 rows are contiguous in global memory
+        const R* st = sm.stage_r();
+        R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
+        for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
+    } else {
+        write_kin<VEC>(sm.stage_f(), reinterpret_cast<float*>(a.obs_out), row0, rows, a.W);
     }
 
     if (a.auto_reset && t == 0) {       // fold this block's partial statistics into its own slot (no global atomics)
@@ -468,7 +511,7 @@ reset_kernel(const __grid_constant__ StepArgs<R> a)
     const int64_t e = (int64_t)blockIdx.x * a.EPB + le;
 
     if (!ctrl && a.obs_out)
-        copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), nullptr, row0, rows, a.W, a.A, a.B, false);
+        copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), nullptr, row0, rows, a.W, a.A, a.B, false, t, (int)blockDim.x);
 
     State<R> s;
     s.px = s.py = s.pz = s.qx = s.qy = s.qz = R(0); s.qw = R(1);
@@ -675,7 +718,7 @@ rollout_pid_kernel(const __grid_constant__ StepArgs<R> a, int n_steps, const R* 
         make_forcing(P, rpm, F);
         for (int sub = 0; sub < a.S; ++sub) {
             R m[9];
-            quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);
+            const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);
             R gnd[4], fb[3] = { R(0), R(0), R(0) };
             const R* pg = nullptr;
             const R* pb = nullptr;
@@ -688,7 +731,7 @@ rollout_pid_kernel(const __grid_constant__ StepArgs<R> a, int n_steps, const R* 
                 drag_body(P, sub == 0 ? rpm_prev : rpm_r, m, s.vx, s.vy, s.vz, fb);
                 pb = fb;
             }
-            dyn_substep<R>(P, a.dt, s, m, F, pg, pb, avx, avy, avz);
+            dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, true, avx, avy, avz);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) rpm_prev[k] = rpm_r[k];

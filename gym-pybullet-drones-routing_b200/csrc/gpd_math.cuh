@@ -47,10 +47,12 @@ template <typename R> __device__ __forceinline__ R clip(R v, R lo, R hi) { retur
 
 // b3Matrix3x3::setRotation as reached through p.getMatrixFromQuaternion (BaseAviary.py:836); row-major m[9].
 template <typename R>
-__device__ __forceinline__ void quat_to_mat(R x, R y, R z, R w, R* m)
+__device__ __forceinline__ R quat_to_mat(R x, R y, R z, R w, R* m)
 {
     R d = x * x + y * y + z * z + w * w;
-    R s = R(2) / d;
+    R s;
+    if constexpr (M<R>::is_double) s = R(2) / d;
+    else s = __fdividef(2.0f, d);      // FP32 throughput mode: MUFU.RCP (2 ulp) instead of the IEEE division sequence
     R xs = x * s, ys = y * s, zs = z * s;
     R wx = w * xs, wy = w * ys, wz = w * zs;
     R xx = x * xs, xy = x * ys, xz = x * zs;
@@ -58,6 +60,7 @@ __device__ __forceinline__ void quat_to_mat(R x, R y, R z, R w, R* m)
     m[0] = R(1) - (yy + zz); m[1] = xy - wz;          m[2] = xz + wy;
     m[3] = xy + wz;          m[4] = R(1) - (xx + zz); m[5] = yz - wx;
     m[6] = xz - wy;          m[7] = yz + wx;          m[8] = R(1) - (xx + yy);
+    return xx + yy;                    // 1 - m[8] without the cancellation (used by the FP32 gravity term)
 }
 
 // pybullet_getEulerFromQuaternion (BaseAviary.py:518, DSLPIDControl.py:144,241)
@@ -98,13 +101,32 @@ template <typename R>
 __device__ __forceinline__ void integrate_q(State<R>& s, R dt)
 {
     R p = s.wx, q = s.wy, r = s.wz;
-    R n = M<R>::sqrt(p * p + q * q + r * r);                     // :877
-    if (n <= R(1e-8)) return;                                    // :879 np.isclose(n, 0): |n| <= atol
-    R theta = n * dt / R(2);                                     // :887
-    R sn, cs;
-    M<R>::sincos(theta, &sn, &cs);
-    R k = R(2) / n;
-    R ap = k * (p * R(.5)) * sn, aq = k * (q * R(.5)) * sn, ar = k * (r * R(.5)) * sn;   // :881-888
+    R cs, ap, aq, ar;
+    bool series = false;
+    if constexpr (!M<R>::is_double) {
+        // FP32 throughput mode.  With theta = |omega|*dt/2 the update matrix is cos(theta)*I + (sin(theta)/|omega|)*Lambda:
+        // both coefficients are even power series in theta, i.e. polynomials in t = theta^2 = |omega|^2*(dt/2)^2, so the
+        // sqrt, the division and sincosf of the literal form disappear.  Truncation error < 3e-10 for theta < 0.5 rad
+        // (|omega| < 240 rad/s at 240 Hz); above that the literal path below is taken.  For |omega| <= 1e-8 (:879) the
+        // series changes q by < 1e-10 relative, below FP32 resolution.
+        R h = dt * R(.5);
+        R t = (p * p + q * q + r * r) * (h * h);
+        if (t < R(0.25)) {
+            series = true;
+            cs = R(1) + t * (R(-1. / 2) + t * (R(1. / 24) + t * (R(-1. / 720) + t * R(1. / 40320))));
+            R sc = h * (R(1) + t * (R(-1. / 6) + t * (R(1. / 120) + t * (R(-1. / 5040) + t * R(1. / 362880)))));
+            ap = p * sc; aq = q * sc; ar = r * sc;
+        }
+    }
+    if (!series) {
+        R n = M<R>::sqrt(p * p + q * q + r * r);                 // :877
+        if (n <= R(1e-8)) return;                                // :879 np.isclose(n, 0): |n| <= atol
+        R theta = n * dt / R(2);                                 // :887
+        R sn;
+        M<R>::sincos(theta, &sn, &cs);
+        R k = R(2) / n;
+        ap = k * (p * R(.5)) * sn; aq = k * (q * R(.5)) * sn; ar = k * (r * R(.5)) * sn;   // :881-888
+    }
     R x = s.qx, y = s.qy, z = s.qz, w = s.qw;
     s.qx = cs * x + ar * y - aq * z + ap * w;
     s.qy = -ar * x + cs * y + ap * z + aq * w;
@@ -217,8 +239,9 @@ __device__ __forceinline__ R downwash_pair(const DevDrone<R>& P, R mx, R my, R m
 //   fb       extra body-frame force (drag + downwash) or nullptr
 //   av*      ang_v = R(old)·rates(new)  (BaseAviary.py:870)
 template <typename R>
-__device__ __forceinline__ void dyn_substep(const DevDrone<R>& P, R dt, State<R>& s, const R* m, const Forcing<R>& F,
-                                            const R* gnd, const R* fb, R& avx, R& avy, R& avz)
+__device__ __forceinline__ void dyn_substep(const DevDrone<R>& P, R dt, State<R>& s, const R* m, R one_minus_m8,
+                                            const Forcing<R>& F, const R* gnd, const R* fb, bool want_av,
+                                            R& avx, R& avy, R& avz)
 {
     R T = F.T, tx = F.tx, ty = F.ty, tz = F.tz;
     R Fx, Fy, Fz;
@@ -237,14 +260,11 @@ __device__ __forceinline__ void dyn_substep(const DevDrone<R>& P, R dt, State<R>
             if (P.model == GPD_CF2P) { tx += (gnd[1] - gnd[3]) * P.L; ty += (-gnd[0] + gnd[2]) * P.L; }
             else { tx += (gnd[0] + gnd[1] - gnd[2] - gnd[3]) * P.ARM; ty += (-gnd[0] + gnd[1] + gnd[2] - gnd[3]) * P.ARM; }
         }
-        // R[:,2]*(T_total) - [0,0,G] = R[:,2]*(T_total - G) + G*(R02, R12, R22 - 1);  R22 - 1 = m[8] - 1 exactly
-        // representable as -(xx+yy): recompute it from the quaternion to avoid the cancellation.
-        R d = s.qx * s.qx + s.qy * s.qy + s.qz * s.qz + s.qw * s.qw;
-        R sc = R(2) / d;
-        R r22m1 = -((s.qx * s.qx + s.qy * s.qy) * sc);
+        // R[:,2]*T_total - [0,0,G] = R[:,2]*(T_total - G) + G*(R02, R12, R22 - 1), with R22 - 1 = -(xx+yy) taken
+        // from quat_to_mat before the "1 -" so that nothing cancels near hover.
         Fx = m[2] * T + P.GRAVITY * m[2];
         Fy = m[5] * T + P.GRAVITY * m[5];
-        Fz = m[8] * T + P.GRAVITY * r22m1;
+        Fz = m[8] * T - P.GRAVITY * one_minus_m8;
     }
     if (fb) {                                                    // CoM LINK-frame forces -> world = R·fb
         Fx = Fx + ((m[0] * fb[0] + m[1] * fb[1]) + m[2] * fb[2]);
@@ -254,15 +274,22 @@ __device__ __forceinline__ void dyn_substep(const DevDrone<R>& P, R dt, State<R>
     // :852-853 torques - cross(rates, J·rates)
     R Jx = P.J[0] * s.wx, Jy = P.J[1] * s.wy, Jz = P.J[2] * s.wz;
     R gx = s.wy * Jz - s.wz * Jy, gy = s.wz * Jx - s.wx * Jz, gz = s.wx * Jy - s.wy * Jx;
-    R dwx = P.JINV[0] * (tx - gx), dwy = P.JINV[1] * (ty - gy), dwz = P.JINV[2] * (tz - gz);   // :854
-    R ax = Fx / P.M, ay = Fy / P.M, az = Fz / P.M;                                         // :855
-    s.vx = s.vx + dt * ax; s.vy = s.vy + dt * ay; s.vz = s.vz + dt * az;                   // :857
-    s.wx = s.wx + dt * dwx; s.wy = s.wy + dt * dwy; s.wz = s.wz + dt * dwz;                // :858
+    if constexpr (M<R>::is_double) {
+        R dwx = P.JINV[0] * (tx - gx), dwy = P.JINV[1] * (ty - gy), dwz = P.JINV[2] * (tz - gz);   // :854
+        R ax = Fx / P.M, ay = Fy / P.M, az = Fz / P.M;                                     // :855
+        s.vx = s.vx + dt * ax; s.vy = s.vy + dt * ay; s.vz = s.vz + dt * az;               // :857
+        s.wx = s.wx + dt * dwx; s.wy = s.wy + dt * dwy; s.wz = s.wz + dt * dwz;            // :858
+    } else {                                                     // same updates with dt/M and dt*J^-1 folded on the host
+        s.vx = s.vx + P.DT_INV_M * Fx; s.vy = s.vy + P.DT_INV_M * Fy; s.vz = s.vz + P.DT_INV_M * Fz;
+        s.wx = s.wx + P.DT_JINV[0] * (tx - gx); s.wy = s.wy + P.DT_JINV[1] * (ty - gy); s.wz = s.wz + P.DT_JINV[2] * (tz - gz);
+    }
     s.px = s.px + dt * s.vx; s.py = s.py + dt * s.vy; s.pz = s.pz + dt * s.vz;             // :859
     integrate_q(s, dt);                                                                    // :860
-    avx = (m[0] * s.wx + m[1] * s.wy) + m[2] * s.wz;                                       // :870
-    avy = (m[3] * s.wx + m[4] * s.wy) + m[5] * s.wz;
-    avz = (m[6] * s.wx + m[7] * s.wy) + m[8] * s.wz;
+    if (want_av) {                                               // only the last substep's value is observable
+        avx = (m[0] * s.wx + m[1] * s.wy) + m[2] * s.wz;                                   // :870
+        avy = (m[3] * s.wx + m[4] * s.wy) + m[5] * s.wz;
+        avz = (m[6] * s.wx + m[7] * s.wy) + m[8] * s.wz;
+    }
 }
 
 // DSLPIDControl.computeControl (control/DSLPIDControl.py:82-259).  st[9] = integral_pos_e, integral_rpy_e, last_rpy.

@@ -63,6 +63,19 @@ def case_setup(g):
     return kw
 
 
+def default_targets(kw):
+    """TARGET_POS of HoverAviary.py:51 / MultiHoverAviary.py:71 from the DEFAULT initial poses."""
+    dp = load_drone_params(kw["model"])
+    n = kw["num_drones"]
+    if kw["env_kind"] == "hover":
+        return np.array([[0., 0., 1.]])
+    if kw["env_kind"] == "multihover":
+        init = np.stack([np.array([x * 4 * dp.L for x in range(n)]), np.array([y * 4 * dp.L for y in range(n)]),
+                         np.ones(n) * (dp.COLLISION_H / 2 - dp.COLLISION_Z_OFFSET + .1)], axis=1)
+        return init + np.array([[0, 0, 1 / (i + 1)] for i in range(n)])
+    return None
+
+
 def make_oracle(kw, num_envs=1):
     from oracle import oracle as orc
     dp = load_drone_params(kw["model"])
@@ -70,4 +83,4 @@ def make_oracle(kw, num_envs=1):
     return orc.OracleSim(dp, num_envs, num_drones=kw["num_drones"], env_kind=kw["env_kind"],
                          action_type=kw["action_type"], pyb_freq=kw["pyb_freq"], ctrl_freq=kw["ctrl_freq"],
                          physics_flags=kw["physics_flags"], pid_params=pid, init_xyz=kw["init_xyz"],
-                         init_rpy=kw["init_rpy"])
+                         init_rpy=kw["init_rpy"], target_pos=default_targets(kw))

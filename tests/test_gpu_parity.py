@@ -6,8 +6,8 @@ import pytest
 
 torch = pytest.importorskip("torch")
 
-from helpers import (S_ANGV, S_POS, S_QUAT, S_RATES, S_RPM, S_RPY, S_VEL, angle_err, case_setup, load_golden,
-                     make_oracle, quat_err, rel_err, traj_cases)
+from helpers import (S_ANGV, S_POS, S_QUAT, S_RATES, S_RPM, S_RPY, S_VEL, angle_err, case_setup, default_targets,
+                     load_golden, make_oracle, quat_err, rel_err, traj_cases)
 from gpd_b200.params import default_pid_params, load_drone_params
 from gpd_b200.utils.enums import DroneModel
 
@@ -20,13 +20,7 @@ def make_sim(kw, num_envs=1, precision="f64", auto_reset=False, tpb=0):
     from gpd_b200.sim import BatchedSim
     dp = load_drone_params(kw["model"])
     n = kw["num_drones"]
-    target = None
-    if kw["env_kind"] == "hover":
-        target = np.array([[0., 0., 1.]])
-    elif kw["env_kind"] == "multihover":
-        init = np.stack([np.array([x * 4 * dp.L for x in range(n)]), np.array([y * 4 * dp.L for y in range(n)]),
-                         np.ones(n) * (dp.COLLISION_H / 2 - dp.COLLISION_Z_OFFSET + .1)], axis=1)
-        target = init + np.array([[0, 0, 1 / (i + 1)] for i in range(n)])
+    target = default_targets(kw)
     return BatchedSim(dp, num_envs, n, env_kind=kw["env_kind"], action_type=kw["action_type"], pyb_freq=kw["pyb_freq"],
                       ctrl_freq=kw["ctrl_freq"], physics_flags=kw["physics_flags"], precision=precision,
                       auto_reset=auto_reset, target_pos=target, init_xyz=kw["init_xyz"], init_rpy=kw["init_rpy"],
