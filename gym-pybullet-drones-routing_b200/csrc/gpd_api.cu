@@ -5,18 +5,39 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "gpd_internal.h"
 
 namespace gpd {
-cudaError_t launch_stats(const double* slots, int64_t nslots, double* out8, int clear, double* slots_mut, cudaStream_t st);
+cudaError_t launch_stats(const StatSlot* slots, int64_t nslots, double* out8, int clear, StatSlot* slots_mut, cudaStream_t st);
 }
 
 using namespace gpd;
 
 static thread_local char g_err[512] = "";
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn()
+{
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
 
 static int fail(int code, const char* fmt, ...)
 {
@@ -41,6 +62,7 @@ struct gpd_sim {
     int64_t D;
     LaunchCfg lc;
     int dpb = 0;
+    int copy_threads = 0;
     std::vector<void*> allocs;
     StepArgs<float> a32;
     StepArgs<double> a64;
@@ -55,7 +77,30 @@ struct gpd_sim {
     int h_cur = 0;
     bool h_has_prev = false;
     double* stats_out = nullptr;
+    // TMA: one tensor map per observation buffer the caller has passed (2-D [D rows][W floats], box [DPB][(B-1)*4])
+    bool tma_ok = false;
+    int tma_bytes = 0, tma_bytes_box = 0;
+    std::unordered_map<const void*, CUtensorMap> tmaps;
 };
+
+static const CUtensorMap* get_tmap(gpd_sim* s, const void* base)
+{
+    auto it = s->tmaps.find(base);
+    if (it != s->tmaps.end()) return &it->second;
+    encode_tiled_fn enc = get_encode_fn();
+    if (!enc || ((uintptr_t)base & 15)) return nullptr;
+    if (s->tmaps.size() > 64) s->tmaps.clear();
+    CUtensorMap tm;
+    cuuint64_t gdim[2] = { (cuuint64_t)s->W, (cuuint64_t)s->D };
+    cuuint64_t gstr[1] = { (cuuint64_t)s->W * 4 };
+    cuuint32_t box[2] = { (cuuint32_t)((s->B - 1) * 4), (cuuint32_t)s->dpb };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nullptr;
+    return &s->tmaps.emplace(base, tm).first->second;
+}
 
 static int action_width(int act)
 {
@@ -99,7 +144,7 @@ static void fill_pid(const gpd_pid_params& p, DevPid<R>& c)
 static size_t smem_bytes(bool f64, bool ctrl, bool multi, int DPB, int EPB)
 {
     size_t rs = f64 ? 8 : 4;
-    size_t stage = ctrl ? (size_t)DPB * 20 * rs : (size_t)DPB * 12 * 4;
+    size_t stage = ctrl ? (size_t)DPB * 20 * rs : 0;
     size_t b = (stage + 15) & ~size_t(15);
     if (multi) b += (size_t)DPB * 3 * rs + (size_t)DPB * 2 * rs + (size_t)DPB * 4 + (size_t)EPB * 2 * 4;
     b += 32;
@@ -164,6 +209,13 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.env_kind = c.env_kind; a.action_type = c.action_type; a.phy = c.physics_flags; a.auto_reset = c.auto_reset;
     a.dt = (R)(1.0 / c.pyb_freq); a.ctrl_dt = (R)(1.0 / c.ctrl_freq); a.speed_limit = (R)c.speed_limit;
     a.pyb_freq = (double)c.pyb_freq; a.episode_len = c.episode_len_sec;
+    {   // `step_counter/PYB_FREQ > EPISODE_LEN_SEC` in Python float arithmetic (HoverAviary.py:114) as an integer test
+        double guess = std::floor(c.episode_len_sec * c.pyb_freq);
+        long long k = guess > 2e9 ? 2000000000LL : (guess < 0 ? 0 : (long long)guess);
+        while (k > 0 && (double)k / (double)c.pyb_freq > c.episode_len_sec) --k;
+        while (k < 2000000000LL && (double)(k + 1) / (double)c.pyb_freq <= c.episode_len_sec) ++k;
+        a.max_counter = (int32_t)k;
+    }
     fill_drone(c.drone, a.drone);
     a.drone.DT_INV_M = (R)((1.0 / c.pyb_freq) / c.drone.M);
     for (int k = 0; k < 3; ++k) a.drone.DT_JINV[k] = (R)((1.0 / c.pyb_freq) * c.drone.J_INV[k]);
@@ -186,13 +238,13 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     if ((rc = dev_alloc(s, &cnt, (size_t)c.num_envs))) return rc;
     a.p.counter = cnt;
     if (c.auto_reset) {
-        float* er; int32_t* el; double* slots;
+        float* er; int32_t* el; StatSlot* slots;
         if ((rc = dev_alloc(s, &er, (size_t)c.num_envs))) return rc;
         if ((rc = dev_alloc(s, &el, (size_t)c.num_envs))) return rc;
-        if ((rc = dev_alloc(s, &slots, (size_t)s->lc.grid * 8))) return rc;
-        std::vector<double> init((size_t)s->lc.grid * 8, 0.0);
-        for (int64_t k = 0; k < s->lc.grid; ++k) { init[k * 8 + 4] = 1e300; init[k * 8 + 5] = -1e300; }
-        CU(cudaMemcpy(slots, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if ((rc = dev_alloc(s, &slots, (size_t)s->lc.grid))) return rc;
+        std::vector<StatSlot> init((size_t)s->lc.grid);
+        for (auto& q : init) { for (double& v : q.s) v = 0.0; q.mn = 0x7fffffff; q.mx = (int32_t)0x80000000; }
+        CU(cudaMemcpy(slots, init.data(), init.size() * sizeof(StatSlot), cudaMemcpyHostToDevice));
         a.p.ep_ret = er; a.p.ep_len = el; a.p.stat_slots = slots;
     }
     // targets
@@ -205,6 +257,10 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     CU(cudaMemcpy(dt_, ht.data(), sizeof(V) * c.num_drones, cudaMemcpyHostToDevice));
     a.p.target = dt_;
     a.DPB = s->dpb;
+    a.copy_threads = s->copy_threads;
+    a.tma_bytes = s->tma_bytes;
+    a.tma_bytes_box = s->tma_bytes_box;
+    a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207
     std::vector<double> xyz((size_t)c.num_drones * 3), rpy((size_t)c.num_drones * 3, 0.0);
@@ -268,18 +324,30 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     s->target_host.assign((size_t)cfg->num_drones * 3, 0.0);
     if (cfg->target_pos) memcpy(s->target_host.data(), cfg->target_pos, sizeof(double) * cfg->num_drones * 3);
     s->cfg.target_pos = nullptr;
-    int T = cfg->threads_per_block ? cfg->threads_per_block : 128;
+    // Thread layout: P physics threads (one per drone, whole envs per block) + one DMA/copy warp for the RL envs.
+    int P = cfg->threads_per_block ? cfg->threads_per_block : 128;
     int N = cfg->num_drones;
-    int DPB = T >= N ? (T / N) * N : N;
-    if (DPB > T) T = (DPB + 31) / 32 * 32;
-    // single-drone RL envs: half of the block integrates, the other half streams the action history
-    const bool spec = N == 1 && !ctrl && T >= 64;
-    if (spec) DPB = T / 2;
+    if (N == 1 && P > 128) P = 128;                       // register budget of the single-drone kernels
+    int DPB = P >= N ? (P / N) * N : N;
+    P = (DPB + 31) / 32 * 32;
     int EPB = DPB / N;
-    s->lc.threads = T;
+    const int copy = ctrl ? 0 : 32;
+    s->copy_threads = copy;
+    s->lc.threads = P + copy;
     s->dpb = DPB;
     s->lc.grid = (cfg->num_envs + EPB - 1) / EPB;
-    s->lc.smem = smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
+    s->tma_ok = !ctrl && A == 4 && s->W % 4 == 0 && s->B >= 2 && (s->B - 1) * 4 <= 256 && DPB <= 256 && get_encode_fn() != nullptr;
+    {
+        const char* ev = getenv("GPD_TMA");
+        if (ev && atoi(ev) == 0) s->tma_ok = false;
+    }
+    s->tma_bytes_box = s->tma_ok ? DPB * (s->B - 1) * 16 : 0;
+    s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128;
+    s->lc.smem = (size_t)s->tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
+    {
+        const char* ev = getenv("GPD_PDL");
+        s->lc.pdl = ev ? atoi(ev) : 1;
+    }
     if (s->lc.grid > 0x7fffffffLL) { delete s; return fail(GPD_ERR_INVALID, "too many envs for one launch"); }
     int rc = cfg->precision == GPD_F64 ? build_args(s, s->a64) : build_args(s, s->a32);
     if (rc == GPD_OK) { cudaError_t e = cudaMalloc((void**)&s->stats_out, 8 * sizeof(double)); if (e != cudaSuccess) rc = fail(GPD_ERR_ALLOC, "cudaMalloc failed"); }
@@ -339,16 +407,24 @@ int gpd_step(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_ou
     if (obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
     CU(cudaSetDevice(s->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    const CUtensorMap* tp = nullptr;
+    const CUtensorMap* to = nullptr;
+    if (s->tma_ok && obs_prev) {
+        tp = get_tmap(s, obs_prev);
+        to = get_tmap(s, obs_out);
+        if (tp) tp = get_tmap(s, obs_prev);     // re-fetch: the second insertion may have rehashed the table
+    }
+    const int use_tma = (tp && to) ? 1 : 0;
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
-        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin;
-        CU(launch_step<double>(a, s->lc, st));
+        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
+        CU(launch_step<double>(a, s->lc, tp, to, st));
     } else {
         StepArgs<float> a = s->a32;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
-        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin;
-        CU(launch_step<float>(a, s->lc, st));
+        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
+        CU(launch_step<float>(a, s->lc, tp, to, st));
     }
     return GPD_OK;
 }
@@ -532,7 +608,7 @@ int gpd_episode_stats(gpd_sim* s, double out[8], int clear, void* stream)
     for (int k = 0; k < 8; ++k) out[k] = 0.0;
     if (!s->cfg.auto_reset) return fail(GPD_ERR_INVALID, "episode statistics are kept only with auto_reset");
     CU(cudaSetDevice(s->cfg.device));
-    double* slots = s->cfg.precision == GPD_F64 ? s->a64.p.stat_slots : s->a32.p.stat_slots;
+    StatSlot* slots = s->cfg.precision == GPD_F64 ? s->a64.p.stat_slots : s->a32.p.stat_slots;
     CU(launch_stats(slots, s->lc.grid, s->stats_out, clear, slots, (cudaStream_t)stream));
     CU(cudaMemcpyAsync(out, s->stats_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));

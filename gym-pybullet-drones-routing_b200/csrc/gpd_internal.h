@@ -1,12 +1,20 @@
 // gpd_internal.h — host/device shared declarations of libgpd_b200 (not part of the public ABI).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/gpd.h"
 
 namespace gpd {
+
+// per-block episode-statistics partials: sums {episodes, return, length, return^2, env_steps, terminated} and the
+// min/max episode return as order-preserving int32 images of float32
+struct StatSlot {
+    double s[6];
+    int32_t mn, mx;
+};
 
 template <typename R> struct Vec4;
 template <> struct Vec4<float> { using type = float4; };
@@ -16,17 +24,20 @@ template <> struct Vec4<double> { using type = double4; };
 // cancellation-free rotor prologue (DESIGN.md "FP32 mode").
 template <typename R>
 struct DevDrone {
+    // ---- hot: everything the lean (plain DYN, RPM action) kernel reads, packed into the first constant-bank lines ----
     int model;
-    R M, L, ARM;            // ARM = L/sqrt(2)  (BaseAviary.py:847-848)
-    R KF, KM;
-    R J[3], JINV[3];
+    int _pad;
+    double KF_d, KM_d, GRAVITY_d, L_d, ARM_d, HOVER_RPM_d, MAX_RPM_d;
     R GRAVITY, MAX_RPM;
     R DT_INV_M, DT_JINV[3]; // FP32 mode: PYB_TIMESTEP/M and PYB_TIMESTEP*J^-1 (filled by gpd_create)
+    R J[3], JINV[3];
+    R M, L, ARM;            // ARM = L/sqrt(2)  (BaseAviary.py:847-848)
+    R KF, KM;
+    // ---- cold: force models ----
     R GND_EFF_COEFF, PROP_RADIUS, GND_EFF_H_CLIP;
     R ROTOR[4][3];
     R DRAG[3];
     R DW1, DW2, DW3;
-    double KF_d, KM_d, GRAVITY_d, L_d, ARM_d, HOVER_RPM_d, MAX_RPM_d;
 };
 
 template <typename R>
@@ -53,7 +64,7 @@ struct SimPtrs {
     int32_t* counter;       // [E] BaseAviary.step_counter
     float* ep_ret;          // [E] running episode return (auto_reset only)
     int32_t* ep_len;        // [E]
-    double* stat_slots;     // [grid][8] per-block statistics partials
+    StatSlot* stat_slots;   // [grid] per-block statistics partials (fire-and-forget atomics, no contention)
     const typename Vec4<R>::type* init_pos;   // [N] or [D]  (xyz, 0)
     const typename Vec4<R>::type* init_quat;  // [N] or [D]
     const typename Vec4<R>::type* target;     // [N] (xyz, 0)
@@ -61,14 +72,18 @@ struct SimPtrs {
 
 template <typename R>
 struct StepArgs {
+    // hot scalars first (constant-bank locality: the kernel entry stalls on every distinct 64-byte line it touches)
     int64_t D;              // total drones
     int64_t E;
     int N, S, A, B, W;
     int DPB, EPB;           // drones / envs per block
     int env_kind, action_type, phy, auto_reset, init_per_env;
+    int32_t max_counter;    // largest step_counter with step_counter/PYB_FREQ <= EPISODE_LEN_SEC (HoverAviary.py:114)
+    int32_t copy_threads;   // last threads of the block: they only move the action history (RL envs)
+    int32_t use_tma;        // history moved by TMA tensor copies (needs obs_prev and float4-granular rows)
+    int32_t tma_bytes;      // shared-memory bytes reserved for the TMA tile (multiple of 128)
+    int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1) * 16
     R dt, ctrl_dt, speed_limit;
-    double pyb_freq, episode_len;
-    SimPtrs<R> p;
     const void* actions;
     const float* obs_prev;
     void* obs_out;
@@ -77,18 +92,22 @@ struct StepArgs {
     uint8_t* truncated;
     float* terminal_kin;
     const uint8_t* reset_mask;   // reset kernel only
+    SimPtrs<R> p;
     DevDrone<R> drone;
     DevPid<R> pid;
+    double pyb_freq, episode_len;
 };
 
 struct LaunchCfg {
     int threads;
     int64_t grid;
     size_t smem;
+    int pdl;                // launch step kernels with programmatic stream serialization
 };
 
 // implemented once per precision in gpd_f32.cu / gpd_f64.cu
-template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
+template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
+                                              const CUtensorMap* tm_out, cudaStream_t st);
 template <typename R> cudaError_t launch_reset(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
 template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, R* state20, R* rpy_rates, R* pid_state,
                                                    int32_t* counter, cudaStream_t st);
@@ -106,8 +125,6 @@ template <typename R> cudaError_t launch_downwash(const DevDrone<R>& d, int64_t 
                                                   cudaStream_t st);
 template <typename R> cudaError_t launch_rollout_pid(const StepArgs<R>& a, int n_steps, const R* waypoints, int n_wp,
                                                      int32_t* wp_counters, R* action, cudaStream_t st);
-template <typename R> cudaError_t launch_stats_reduce(const double* slots, int64_t nslots, double* out8,
-                                                      cudaStream_t st);
 
 size_t step_smem_bytes(int precision, int env_kind, int N, int DPB, int EPB);
 

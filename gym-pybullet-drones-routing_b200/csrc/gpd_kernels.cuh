@@ -23,18 +23,60 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p)
     return r;
 }
 
+// Programmatic dependent launch (PDL): a step kernel launched with programmaticStreamSerialization may start while the
+// previous kernel of the stream drains; pdl_wait() blocks until that kernel has completed and its writes are visible,
+// so only the CTA launch, the constant-bank parameter fetch and the shared-memory set-up overlap. No-ops otherwise.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Physics-only barrier (named barrier 1): the DMA/copy warp of the block never joins it.
+__device__ __forceinline__ void phys_sync(int nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
+
+// ---- TMA (cp.async.bulk.tensor) helpers: the action history of a block tile is one 2-D box [rows][(B-1)*16 bytes] ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, const void* smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- shared-memory layout -------------------------------------------------------------
-//   stage : RL envs float[DPB*12] (kin part of each obs row) | Ctrl env R[DPB*20] (state20 rows)
+//   tile  : RL envs with A == 4: TMA box of the action history, DPB x (B-1) float4 (a.tma_bytes)
+//   stage : Ctrl env R[DPB*20] (state20 rows)
 //   MULTI : snap R[DPB*3], red R[DPB*2], redi int[DPB], envf int[EPB*2]
 //   stats : float[4] + int[4]
 template <typename R>
 struct Smem {
-    unsigned char* base;
+    unsigned char* base;     // dynamic shared memory + the TMA history tile (tma_bytes, 128-byte multiple) that precedes everything
     int DPB, EPB;
     bool ctrl, multi;
     __device__ float* stage_f() const { return reinterpret_cast<float*>(base); }
     __device__ R* stage_r() const { return reinterpret_cast<R*>(base); }
-    __device__ size_t stage_bytes() const { return ctrl ? size_t(DPB) * 20 * sizeof(R) : size_t(DPB) * 12 * sizeof(float); }
+    __device__ size_t stage_bytes() const { return ctrl ? size_t(DPB) * 20 * sizeof(R) : 0; }
     __device__ R* snap() const { return reinterpret_cast<R*>(base + ((stage_bytes() + 15) & ~size_t(15))); }
     __device__ R* red() const { return snap() + (multi ? size_t(DPB) * 3 : 0); }
     __device__ int* redi() const { return reinterpret_cast<int*>(red() + (multi ? size_t(DPB) * 2 : 0)); }
@@ -63,86 +105,62 @@ __device__ __forceinline__ void copy_history(const float* __restrict__ prev, flo
                                              const float* __restrict__ act, int64_t row0, int rows, int W, int A, int B,
                                              bool shift, int ct, int CT)
 {
-    constexpr int U = 8;     // independent loads in flight per thread before the first store (memory-level parallelism)
+    constexpr int U = 4;     // independent loads in flight per thread before the first store (memory-level parallelism)
     if constexpr (VEC) {     // A == 4: rows are whole float4s, the shift is one float4
+        // 8 lanes walk one row (8 x 16 B = one 128-byte segment per pass over the columns); index math is one IMAD.
         const int W4 = W >> 2;
-        const float4* prev4 = reinterpret_cast<const float4*>(prev);
-        const float4* act4 = reinterpret_cast<const float4*>(act);
-        float4* out4 = reinterpret_cast<float4*>(out);
-        const int total = rows * B;
-        const int qs = CT / B, rs = CT - qs * B;
-        int row = ct / B, c = ct - row * B;
-        for (int base = ct; base < total; base += U * CT) {
-            float4 v[U];
-            int64_t dst[U];
+        const float4* prev4 = prev ? reinterpret_cast<const float4*>(prev) + row0 * W4 + 3 : nullptr;   // tile base
+        const float4* act4 = reinterpret_cast<const float4*>(act) + row0;
+        float4* out4 = reinterpret_cast<float4*>(out) + row0 * W4 + 3;
+        const int lane_c = ct & 7, r0 = ct >> 3, RS = CT >> 3;      // CT is a multiple of 32
+        const int src_shift = shift ? 1 : 0;
+        for (int c = lane_c; c < B; c += 8) {
+            const bool newest = shift && c == B - 1;
+            for (int rb = r0; rb < rows; rb += RS * U) {
+                float4 v[U];
 #pragma unroll
-            for (int j = 0; j < U; ++j) {
-                dst[j] = -1;
-                if (base + j * CT < total) {
-                    int64_t rbase = (row0 + row) * W4 + 3;
-                    dst[j] = rbase + c;
-                    if (shift) {
-                        if (c < B - 1) v[j] = prev ? ldg_stream(prev4 + rbase + c + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        else v[j] = __ldg(act4 + row0 + row);
-                    } else {
-                        v[j] = prev ? ldg_stream(prev4 + rbase + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < U; ++j) {
+                    const int row = rb + j * RS;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < rows) {
+                        if (newest) v[j] = __ldg(act4 + row);
+                        else if (prev4) v[j] = ldg_stream(prev4 + row * W4 + c + src_shift);
                     }
                 }
-                c += rs; row += qs;
-                if (c >= B) { c -= B; row += 1; }
-            }
 #pragma unroll
-            for (int j = 0; j < U; ++j)
-                if (dst[j] >= 0) out4[dst[j]] = v[j];
+                for (int j = 0; j < U; ++j) {
+                    const int row = rb + j * RS;
+                    if (row < rows) out4[row * W4 + c] = v[j];
+                }
+            }
         }
     } else {
         const int H = A * B, keep = A * (B - 1);
+        const float* prevb = prev ? prev + row0 * (int64_t)W + 12 : nullptr;
+        const float* actb = act + row0 * A;
+        float* outb = out + row0 * (int64_t)W + 12;
         const int total = rows * H;
         const int qs = CT / H, rs = CT - qs * H;
         int row = ct / H, c = ct - row * H;
+        const int src_shift = shift ? A : 0;
         for (int base = ct; base < total; base += U * CT) {
             float v[U];
-            int64_t dst[U];
+            int off[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                dst[j] = -1;
-                if (base + j * CT < total) {
-                    int64_t rbase = (row0 + row) * (int64_t)W + 12;
-                    dst[j] = rbase + c;
-                    if (shift) {
-                        if (c < keep) v[j] = prev ? __ldg(prev + rbase + c + A) : 0.f;
-                        else v[j] = __ldg(act + (row0 + row) * A + (c - keep));
-                    } else {
-                        v[j] = prev ? __ldg(prev + rbase + c) : 0.f;
-                    }
+                off[j] = row * W + c;
+                const bool ok = base + j * CT < total;
+                v[j] = 0.f;
+                if (ok) {
+                    if (shift && c >= keep) v[j] = __ldg(actb + row * A + (c - keep));
+                    else if (prevb) v[j] = __ldg(prevb + off[j] + src_shift);
                 }
                 c += rs; row += qs;
                 if (c >= H) { c -= H; row += 1; }
             }
 #pragma unroll
             for (int j = 0; j < U; ++j)
-                if (dst[j] >= 0) out[dst[j]] = v[j];
-        }
-    }
-}
-
-// Kinematic part of the observation tile (12 floats per row) from the shared staging buffer.
-template <bool VEC>
-__device__ __forceinline__ void write_kin(const float* __restrict__ stage, float* __restrict__ out, int64_t row0, int rows, int W)
-{
-    const int t = threadIdx.x, T = blockDim.x;
-    if constexpr (VEC) {
-        const int W4 = W >> 2;
-        const float4* s4 = reinterpret_cast<const float4*>(stage);
-        float4* out4 = reinterpret_cast<float4*>(out);
-        for (int idx = t; idx < rows * 3; idx += T) {
-            int row = idx / 3, j = idx - row * 3;
-            out4[(row0 + row) * W4 + j] = s4[idx];
-        }
-    } else {
-        for (int idx = t; idx < rows * 12; idx += T) {
-            int row = idx / 12, j = idx - row * 12;
-            out[(row0 + row) * (int64_t)W + j] = stage[idx];
+                if (base + j * CT < total) outb[off[j]] = v[j];
         }
     }
 }
@@ -217,12 +235,14 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
 //   VEC   : A == 4 (observation rows are float4-granular)
 // ============================================================================================
 template <typename R, bool LEAN, bool MULTI, bool VEC>
-__global__ void __launch_bounds__(256)
-step_kernel(const __grid_constant__ StepArgs<R> a)
+__global__ void __launch_bounds__(MULTI ? 288 : 160, MULTI ? 1 : (sizeof(R) == 4 ? 6 : 2))
+step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUtensorMap tm_prev,
+            const __grid_constant__ CUtensorMap tm_out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t tma_bar;
     const bool ctrl = a.env_kind == GPD_ENV_CTRL;
-    Smem<R> sm{ smem_raw, a.DPB, a.EPB, ctrl, MULTI };
+    Smem<R> sm{ smem_raw + a.tma_bytes, a.DPB, a.EPB, ctrl, MULTI };
     const int t = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * a.DPB;
     const int64_t d = row0 + t;
@@ -232,20 +252,33 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     const int i = MULTI ? t - le * a.N : 0;      // drone index in env
     const int64_t e = MULTI ? (int64_t)blockIdx.x * a.EPB + le : d;
     const DevDrone<R>& P = a.drone;
-    // Warp specialisation (single-drone RL envs): threads [0, DPB) integrate the physics, threads [DPB, T) stream the
-    // action history; the two roles overlap instead of queueing behind each other in the same warps.
-    const bool spec = !MULTI && !ctrl && (int)blockDim.x >= 2 * a.DPB;
-    const bool run_physics = !spec || t < a.DPB;
+    // Warp specialisation (RL envs): the last `copy_threads` threads of the block (one warp) move the action history of
+    // the tile — as two TMA tensor copies issued by one lane when the rows are float4-granular — while the other warps
+    // integrate the physics.  The two roles never wait for each other except at the final block barrier.
+    const int nphys = (int)blockDim.x - a.copy_threads;
+    const bool spec = a.copy_threads > 0;
+    const bool run_physics = t < nphys;
 
+    pdl_launch_dependents();
     if (a.auto_reset) {
         if (t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
         __syncthreads();
     }
+    pdl_wait();                         // everything above touched only parameters and shared memory
 
-    if (spec) {
-        if (t >= a.DPB)
+    if (spec && !run_physics) {
+        if (VEC && a.use_tma) {
+            if (t == nphys) {           // one lane drives the TMA engine: global -> shared -> global, shifted by one slot
+                mbar_init(&tma_bar, 1);
+                mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
+                tma_load_2d(smem_raw, &tm_prev, 16, (int)row0, &tma_bar);      // columns 16.. : ring slots 1..B-1 of the old obs
+                mbar_wait(&tma_bar, 0);
+                tma_store_2d(&tm_out, 12, (int)row0, smem_raw);                // columns 12.. : ring slots 0..B-2 of the new obs
+            }
+        } else {
             copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
-                              row0, rows, a.W, a.A, a.B, true, t - a.DPB, (int)blockDim.x - a.DPB);
+                              row0, rows, a.W, a.A, a.B, true, t - nphys, a.copy_threads);
+        }
     }
 
     if (run_physics) {
@@ -256,8 +289,15 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     double rpm[4] = { 0., 0., 0., 0. };
     float act[4] = { 0.f, 0.f, 0.f, 0.f };
     R rpm_prev[4] = { R(0), R(0), R(0), R(0) };
+    int32_t cnt = 0;
+    float ep_ret0 = 0.f;
+    int ep_len0 = 0;
     if (active) {
         load_state(a.p, d, s);
+        if (i == 0) {                   // per-env bookkeeping: loaded here so its DRAM latency hides behind the physics
+            cnt = a.p.counter[e];
+            if (a.auto_reset) { ep_ret0 = a.p.ep_ret[e]; ep_len0 = a.p.ep_len[e]; }
+        }
         if (a.action_type == GPD_ACT_CTRL_RPM) {                 // CtrlAviary.py:140
             V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
             rpm[0] = clip(v.x, R(0), P.MAX_RPM); rpm[1] = clip(v.y, R(0), P.MAX_RPM);
@@ -282,7 +322,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     // ---- action history of the observation: independent of the physics, issue it now ----
     if (!ctrl && !spec)
         copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
-                          row0, rows, a.W, a.A, a.B, true, t, (int)blockDim.x);
+                          row0, rows, a.W, a.A, a.B, true, t, nphys);
 
     // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238) ----
     if (a.action_type == GPD_ACT_RPM) {
@@ -331,9 +371,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
             if constexpr (MULTI) {
                 if (a.phy & GPD_PHY_DW) {                        // :362,367 against the substep-start snapshot
                     R* snap = sm.snap();
-                    __syncthreads();
+                    phys_sync(nphys);
                     if (t < a.DPB) { snap[3 * t] = s.px; snap[3 * t + 1] = s.py; snap[3 * t + 2] = s.pz; }
-                    __syncthreads();
+                    phys_sync(nphys);
                     R dw = R(0);
                     const R* env = snap + 3 * (le * a.N);
                     if (active)
@@ -353,7 +393,6 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
 
     R rew = R(-1);                      // CtrlAviary.py:144-200: dummy reward/flags
     int term = 0, trunc = 0;
-    int32_t cnt = 0;
     if (!ctrl) {
         V4<R> tg = a.p.target[i];
         R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
@@ -367,9 +406,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
         if constexpr (MULTI) {
             R* red = sm.red();
             int* redi = sm.redi();
-            __syncthreads();
+            phys_sync(nphys);
             if (t < a.DPB) { red[2 * t] = active ? r_i : R(0); red[2 * t + 1] = active ? dist : R(0); redi[t] = active ? tr_i : 0; }
-            __syncthreads();
+            phys_sync(nphys);
             if (active && i == 0) {     // in-order sums over the env's drones (MultiHoverAviary.py:86-88,103-105)
                 R rs = R(0), ds = R(0);
                 int tr = 0;
@@ -383,8 +422,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
         }
     }
     if (active && i == 0) {
-        cnt = a.p.counter[e];
-        if (!ctrl && ((double)cnt / a.pyb_freq > a.episode_len)) trunc = 1;   // HoverAviary.py:114, counter BEFORE the increment
+        if (!ctrl && cnt > a.max_counter) trunc = 1;   // HoverAviary.py:114 (counter BEFORE the increment); threshold from the host
         if (a.reward) a.reward[e] = rew;
         if (a.terminated) a.terminated[e] = (uint8_t)term;
         if (a.truncated) a.truncated[e] = (uint8_t)trunc;
@@ -394,9 +432,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
         done = term | trunc;
         if constexpr (MULTI) {
             int* envf = sm.envf();
-            __syncthreads();
+            phys_sync(nphys);
             if (active && i == 0) envf[le] = done;
-            __syncthreads();
+            phys_sync(nphys);
             done = active ? envf[le] : 0;
         }
     }
@@ -408,23 +446,39 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
     kin[9] = (float)avx; kin[10] = (float)avy; kin[11] = (float)avz;
     R out_rpm[4] = { rpm_r[0], rpm_r[1], rpm_r[2], rpm_r[3] };
 
-    if (a.auto_reset && active) {
-        if (i == 0) {                   // Monitor-style episode statistics
-            float er = a.p.ep_ret[e] + (float)rew;
-            int el = a.p.ep_len[e] + 1;
-            if (done) {
-                atomicAdd(&sm.stat_f()[0], er);
-                atomicAdd(&sm.stat_f()[1], er * er);
-                atomicAdd(&sm.stat_i()[0], 1);
-                atomicAdd(&sm.stat_i()[1], el);
-                atomicMin(&sm.stat_i()[2], float_to_ordered(er));
-                atomicMax(&sm.stat_i()[3], float_to_ordered(er));
-                if (term) atomicAdd(&sm.stat_f()[2], 1.f);
-                er = 0.f; el = 0;
+    if (a.auto_reset) {                 // Monitor-style episode statistics (examples/learn.py:53-57 wraps the env in Monitor)
+        const bool lead = active && i == 0;
+        float er = ep_ret0 + (float)rew;
+        int el = ep_len0 + 1;
+        const bool fin = lead && done;
+        const unsigned m = __ballot_sync(0xffffffffu, fin);
+        if (m) {                        // reduce over the warp, then one set of shared-memory atomics per warp
+            float s1 = fin ? er : 0.f, s2 = fin ? er * er : 0.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
             }
-            a.p.ep_ret[e] = er;
-            a.p.ep_len[e] = el;
+            const int nl = __reduce_add_sync(0xffffffffu, fin ? el : 0);
+            const int nt = __popc(__ballot_sync(0xffffffffu, fin && term));
+            const int mn = __reduce_min_sync(0xffffffffu, fin ? float_to_ordered(er) : 0x7fffffff);
+            const int mx = __reduce_max_sync(0xffffffffu, fin ? float_to_ordered(er) : (int)0x80000000);
+            if ((t & 31) == 0) {
+                atomicAdd(&sm.stat_f()[0], s1);
+                atomicAdd(&sm.stat_f()[1], s2);
+                atomicAdd(&sm.stat_i()[0], __popc(m));
+                atomicAdd(&sm.stat_i()[1], nl);
+                atomicMin(&sm.stat_i()[2], mn);
+                atomicMax(&sm.stat_i()[3], mx);
+                if (nt) atomicAdd(&sm.stat_f()[2], (float)nt);
+            }
         }
+        if (lead) {
+            a.p.ep_ret[e] = fin ? 0.f : er;
+            a.p.ep_len[e] = fin ? 0 : el;
+        }
+    }
+    if (a.auto_reset && active) {
         if (done) {
             if (a.terminal_kin && !ctrl) {
                 float4* tk = reinterpret_cast<float4*>(a.terminal_kin) + d * 3;
@@ -456,39 +510,45 @@ step_kernel(const __grid_constant__ StepArgs<R> a)
             r[0] = s.px; r[1] = s.py; r[2] = s.pz; r[3] = s.qx; r[4] = s.qy; r[5] = s.qz; r[6] = s.qw;
             r[7] = roll; r[8] = pitch; r[9] = yaw; r[10] = s.vx; r[11] = s.vy; r[12] = s.vz;
             r[13] = avx; r[14] = avy; r[15] = avz; r[16] = out_rpm[0]; r[17] = out_rpm[1]; r[18] = out_rpm[2]; r[19] = out_rpm[3];
-        } else {
-            float4* r = reinterpret_cast<float4*>(sm.stage_f()) + 3 * t;
-            r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
-            r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
-            r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+        } else if (active) {
+            // KIN observation, BaseRLAviary.py:310-316: 12 float32 at the head of this drone's row.  48 contiguous
+            // bytes per thread; L2 merges them with the history part written by the copy warps.
+            if constexpr (VEC) {
+                float4* r = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.obs_out) + d * a.W);
+                r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
+                r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
+                r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+                r[(a.W >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);   // newest ring slot, BaseRLAviary.py:187
+            } else {
+                float* r = reinterpret_cast<float*>(a.obs_out) + d * a.W;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) r[k] = kin[k];
+            }
         }
     }
     }   // run_physics
 
-    // ---- observation tile: coalesced write of the staged rows by the whole block ----
-    __syncthreads();
-    if (ctrl) {                         // the tile's state20 rows are contiguous in global memory
+    // ---- Ctrl observation tile: coalesced write of the staged state20 rows (contiguous in global memory) ----
+    if (ctrl || a.auto_reset) __syncthreads();
+    if (ctrl) {
         const R* st = sm.stage_r();
         R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
         for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
-    } else {
-        write_kin<VEC>(sm.stage_f(), reinterpret_cast<float*>(a.obs_out), row0, rows, a.W);
     }
 
-    if (a.auto_reset && t == 0) {       // fold this block's partial statistics into its own slot (no global atomics)
-        double* slot = a.p.stat_slots + (int64_t)blockIdx.x * 8;
-        int n = sm.stat_i()[0];
+    if (a.auto_reset && t == 0) {       // fold the block's partials into its own slot: RED (no return value, no wait)
+        StatSlot* slot = a.p.stat_slots + blockIdx.x;
+        const int n = sm.stat_i()[0];
         if (n > 0) {
-            slot[0] += (double)n;
-            slot[1] += (double)sm.stat_f()[0];
-            slot[2] += (double)sm.stat_i()[1];
-            slot[3] += (double)sm.stat_f()[1];
-            double mn = (double)ordered_to_float(sm.stat_i()[2]), mx = (double)ordered_to_float(sm.stat_i()[3]);
-            if (mn < slot[4]) slot[4] = mn;
-            if (mx > slot[5]) slot[5] = mx;
-            slot[7] += (double)sm.stat_f()[2];
+            atomicAdd(&slot->s[0], (double)n);
+            atomicAdd(&slot->s[1], (double)sm.stat_f()[0]);
+            atomicAdd(&slot->s[2], (double)sm.stat_i()[1]);
+            atomicAdd(&slot->s[3], (double)sm.stat_f()[1]);
+            atomicMin(&slot->mn, sm.stat_i()[2]);
+            atomicMax(&slot->mx, sm.stat_i()[3]);
+            if (sm.stat_f()[2] > 0.f) atomicAdd(&slot->s[5], (double)sm.stat_f()[2]);
         }
-        slot[6] += (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)blockIdx.x * a.EPB) : rows);
+        atomicAdd(&slot->s[4], (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)blockIdx.x * a.EPB) : rows));
     }
 }
 
@@ -501,7 +561,7 @@ reset_kernel(const __grid_constant__ StepArgs<R> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const bool ctrl = a.env_kind == GPD_ENV_CTRL;
-    Smem<R> sm{ smem_raw, a.DPB, a.EPB, ctrl, false };
+    Smem<R> sm{ smem_raw + a.tma_bytes, a.DPB, a.EPB, ctrl, false };
     const int t = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * a.DPB;
     const int64_t d = row0 + t;
@@ -550,16 +610,19 @@ reset_kernel(const __grid_constant__ StepArgs<R> a)
         __syncthreads();
         R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
         for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
-    } else {
-        float* st = sm.stage_f();
-        if (t < a.DPB) {
-            float4* r = reinterpret_cast<float4*>(st) + 3 * t;
-            r[0] = make_float4((float)s.px, (float)s.py, (float)s.pz, (float)roll);
-            r[1] = make_float4((float)pitch, (float)yaw, (float)s.vx, (float)s.vy);
-            r[2] = make_float4((float)s.vz, (float)avx, (float)avy, (float)avz);
+    } else if (active) {                // KIN part of the row, BaseRLAviary.py:310-316 (the ring part was copied above)
+        const float kin[12] = { (float)s.px, (float)s.py, (float)s.pz, (float)roll, (float)pitch, (float)yaw,
+                                (float)s.vx, (float)s.vy, (float)s.vz, (float)avx, (float)avy, (float)avz };
+        float* r = reinterpret_cast<float*>(a.obs_out) + d * a.W;
+        if constexpr (VEC) {
+            float4* r4 = reinterpret_cast<float4*>(r);
+            r4[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
+            r4[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
+            r4[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) r[k] = kin[k];
         }
-        __syncthreads();
-        write_kin<VEC>(st, reinterpret_cast<float*>(a.obs_out), row0, rows, a.W);
     }
 }
 
