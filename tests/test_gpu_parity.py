@@ -368,3 +368,48 @@ def test_cuda_rollout_pid_matches_stepwise_loop():
     assert rel_err(xa[0][..., 0:3].cpu().numpy(), ref.state20[..., 0:3]) <= 1e-7
     assert rel_err(act_a.cpu().numpy(), act_o) <= 1e-6
     sa.close(); sb.close()
+
+
+def test_cuda_vec_env_protocol():
+    """SB3 VecEnv contract over the batched env: numpy in/out, auto-reset, terminal_observation, TimeLimit.truncated,
+    Monitor-style episode infos — checked against the oracle stepped with the same actions."""
+    from gpd_b200.envs import HoverAviary
+    from gpd_b200.vec_env import GpdVecEnv
+    rng = np.random.default_rng(21)
+    E = 96
+    venv = GpdVecEnv(HoverAviary, E, precision="f64")
+    assert venv.num_envs == E and venv.observation_space.shape == (1, 72) and venv.action_space.shape == (1, 4)
+    kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    ref = make_oracle(kw, num_envs=E)
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (E, 1, 72) and obs.dtype == np.float32
+    ep_r = np.zeros(E); ep_l = np.zeros(E, int)
+    seen_done = 0
+    for t in range(40):
+        a = rng.uniform(-1, 1, size=(E, 1, 4)).astype(np.float32)
+        obs, rew, dones, infos = venv.step(a)
+        o_ref, r_ref, te_ref, tr_ref = ref.step(a)
+        o_ref = o_ref.copy()
+        d_ref = (te_ref | tr_ref).astype(bool)
+        assert np.array_equal(dones, d_ref) and len(infos) == E
+        np.testing.assert_allclose(rew, r_ref, rtol=1e-9, atol=1e-12)
+        ep_r += r_ref; ep_l += 1
+        for e in np.nonzero(d_ref)[0]:
+            info = infos[int(e)]
+            np.testing.assert_allclose(info["terminal_observation"], o_ref[e], rtol=1e-6, atol=1e-6)
+            assert info["TimeLimit.truncated"] == bool(tr_ref[e] and not te_ref[e])
+            assert abs(info["episode"]["r"] - ep_r[e]) <= 1e-9 * max(1, abs(ep_r[e])) and info["episode"]["l"] == ep_l[e]
+            ep_r[e] = 0; ep_l[e] = 0
+            seen_done += 1
+        not_done = np.nonzero(~d_ref)[0]
+        if len(not_done):
+            assert "terminal_observation" not in infos[int(not_done[0])]
+        if d_ref.any():
+            o_ref[d_ref] = ref.reset(d_ref.astype(np.uint8))[d_ref]
+        np.testing.assert_allclose(obs, o_ref, rtol=1e-6, atol=1e-6)
+    assert seen_done > 0
+    assert venv.env_is_wrapped(object) == [False] * E and venv.get_attr("CTRL_FREQ")[0] == 30
+    o, r, te, tr = venv.step_tensor(torch.zeros((E, 1, 4), device="cuda"))
+    assert o.is_cuda and o.shape == (E, 1, 72) and te.dtype == torch.bool
+    venv.close()
