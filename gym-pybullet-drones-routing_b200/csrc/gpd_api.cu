@@ -79,7 +79,7 @@ struct gpd_sim {
     double* stats_out = nullptr;
     // TMA: one tensor map per observation buffer the caller has passed (2-D [D rows][W floats], box [DPB][(B-1)*4])
     bool tma_ok = false;
-    int tma_bytes = 0, tma_bytes_box = 0;
+    int tma_bytes = 0, tma_bytes_box = 0, tma_edge = 0;
     std::unordered_map<const void*, CUtensorMap> tmaps;
 };
 
@@ -93,7 +93,7 @@ static const CUtensorMap* get_tmap(gpd_sim* s, const void* base)
     CUtensorMap tm;
     cuuint64_t gdim[2] = { (cuuint64_t)s->W, (cuuint64_t)s->D };
     cuuint64_t gstr[1] = { (cuuint64_t)s->W * 4 };
-    cuuint32_t box[2] = { (cuuint32_t)((s->B - 1) * 4), (cuuint32_t)s->dpb };
+    cuuint32_t box[2] = { (cuuint32_t)((s->B - 1 - 2 * s->tma_edge) * 4), (cuuint32_t)s->dpb };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -238,14 +238,13 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     if ((rc = dev_alloc(s, &cnt, (size_t)c.num_envs))) return rc;
     a.p.counter = cnt;
     if (c.auto_reset) {
-        float* er; int32_t* el; StatSlot* slots;
+        float* er; StatSlot* slots;
         if ((rc = dev_alloc(s, &er, (size_t)c.num_envs))) return rc;
-        if ((rc = dev_alloc(s, &el, (size_t)c.num_envs))) return rc;
         if ((rc = dev_alloc(s, &slots, (size_t)s->lc.grid))) return rc;
         std::vector<StatSlot> init((size_t)s->lc.grid);
         for (auto& q : init) { for (double& v : q.s) v = 0.0; q.mn = 0x7fffffff; q.mx = (int32_t)0x80000000; }
         CU(cudaMemcpy(slots, init.data(), init.size() * sizeof(StatSlot), cudaMemcpyHostToDevice));
-        a.p.ep_ret = er; a.p.ep_len = el; a.p.stat_slots = slots;
+        a.p.ep_ret = er; a.p.stat_slots = slots;
     }
     // targets
     std::vector<V> ht((size_t)c.num_drones);
@@ -260,6 +259,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.copy_threads = s->copy_threads;
     a.tma_bytes = s->tma_bytes;
     a.tma_bytes_box = s->tma_bytes_box;
+    a.tma_edge = s->tma_edge;
     a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207
@@ -325,8 +325,9 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     if (cfg->target_pos) memcpy(s->target_host.data(), cfg->target_pos, sizeof(double) * cfg->num_drones * 3);
     s->cfg.target_pos = nullptr;
     // Thread layout: P physics threads (one per drone, whole envs per block) + one DMA/copy warp for the RL envs.
-    int P = cfg->threads_per_block ? cfg->threads_per_block : 128;
     int N = cfg->num_drones;
+    // default: 64 physics threads for single-drone envs (more, smaller CTAs balance better over 148 SMs), 128 otherwise
+    int P = cfg->threads_per_block ? cfg->threads_per_block : (N == 1 ? 64 : 128);
     if (N == 1 && P > 128) P = 128;                       // register budget of the single-drone kernels
     int DPB = P >= N ? (P / N) * N : N;
     P = (DPB + 31) / 32 * 32;
@@ -341,7 +342,15 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         const char* ev = getenv("GPD_TMA");
         if (ev && atoi(ev) == 0) s->tma_ok = false;
     }
-    s->tma_bytes_box = s->tma_ok ? DPB * (s->B - 1) * 16 : 0;
+    // whole-sector split of the row between the drone's thread and TMA: pays off once the launch is DRAM-bound; below
+    // ~256k drones the launch is latency-bound and the two extra strided loads per thread cost more than the fills
+    s->tma_edge = (s->tma_ok && (s->W / 4) % 2 == 0 && s->B >= 4 && s->D >= 262144) ? 1 : 0;
+    {
+        const char* ev = getenv("GPD_TMA_EDGE");
+        if (ev && atoi(ev) == 0) s->tma_edge = 0;
+        if (ev && atoi(ev) == 1 && s->tma_ok && (s->W / 4) % 2 == 0 && s->B >= 4) s->tma_edge = 1;
+    }
+    s->tma_bytes_box = s->tma_ok ? DPB * (s->B - 1 - 2 * s->tma_edge) * 16 : 0;
     s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128;
     s->lc.smem = (size_t)s->tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
     {

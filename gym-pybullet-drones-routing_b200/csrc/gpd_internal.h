@@ -63,7 +63,6 @@ struct SimPtrs {
     R* pid;
     int32_t* counter;       // [E] BaseAviary.step_counter
     float* ep_ret;          // [E] running episode return (auto_reset only)
-    int32_t* ep_len;        // [E]
     StatSlot* stat_slots;   // [grid] per-block statistics partials (fire-and-forget atomics, no contention)
     const typename Vec4<R>::type* init_pos;   // [N] or [D]  (xyz, 0)
     const typename Vec4<R>::type* init_quat;  // [N] or [D]
@@ -82,7 +81,8 @@ struct StepArgs {
     int32_t copy_threads;   // last threads of the block: they only move the action history (RL envs)
     int32_t use_tma;        // history moved by TMA tensor copies (needs obs_prev and float4-granular rows)
     int32_t tma_bytes;      // shared-memory bytes reserved for the TMA tile (multiple of 128)
-    int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1) * 16
+    int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1-2*tma_edge) * 16
+    int32_t tma_edge;       // 1: rows are 32-byte aligned, the box skips the first and last shifted slot (written by the drone's thread)
     R dt, ctrl_dt, speed_limit;
     const void* actions;
     const float* obs_prev;

@@ -271,9 +271,12 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             if (t == nphys) {           // one lane drives the TMA engine: global -> shared -> global, shifted by one slot
                 mbar_init(&tma_bar, 1);
                 mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
-                tma_load_2d(smem_raw, &tm_prev, 16, (int)row0, &tma_bar);      // columns 16.. : ring slots 1..B-1 of the old obs
+                // box = ring slots [edge, B-1-edge) of the new obs = slots [edge+1, B-edge) of the old one.  edge = 1 when the
+                // rows are 32-byte aligned: the two sectors shared with the kin part / the newest slot are then written
+                // whole by the drone's own thread (no partial-sector L2 fills from DRAM).
+                tma_load_2d(smem_raw, &tm_prev, 12 + 4 * (a.tma_edge + 1), (int)row0, &tma_bar);
                 mbar_wait(&tma_bar, 0);
-                tma_store_2d(&tm_out, 12, (int)row0, smem_raw);                // columns 12.. : ring slots 0..B-2 of the new obs
+                tma_store_2d(&tm_out, 12 + 4 * a.tma_edge, (int)row0, smem_raw);
             }
         } else {
             copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
@@ -291,12 +294,19 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     R rpm_prev[4] = { R(0), R(0), R(0), R(0) };
     int32_t cnt = 0;
     float ep_ret0 = 0.f;
-    int ep_len0 = 0;
+    float4 edge_lo = make_float4(0.f, 0.f, 0.f, 0.f), edge_hi = edge_lo;     // old ring slots 1 and B-1 (see the DMA warp)
     if (active) {
         load_state(a.p, d, s);
         if (i == 0) {                   // per-env bookkeeping: loaded here so its DRAM latency hides behind the physics
             cnt = a.p.counter[e];
-            if (a.auto_reset) { ep_ret0 = a.p.ep_ret[e]; ep_len0 = a.p.ep_len[e]; }
+            if (a.auto_reset) ep_ret0 = a.p.ep_ret[e];
+        }
+        if constexpr (VEC) {
+            if (a.use_tma && a.tma_edge && a.obs_prev) {
+                const float4* pr = reinterpret_cast<const float4*>(a.obs_prev + d * a.W);
+                edge_lo = ldg_stream(pr + 4);
+                edge_hi = ldg_stream(pr + (a.W >> 2) - 1);
+            }
         }
         if (a.action_type == GPD_ACT_CTRL_RPM) {                 // CtrlAviary.py:140
             V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
@@ -449,7 +459,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     if (a.auto_reset) {                 // Monitor-style episode statistics (examples/learn.py:53-57 wraps the env in Monitor)
         const bool lead = active && i == 0;
         float er = ep_ret0 + (float)rew;
-        int el = ep_len0 + 1;
+        int el = cnt / a.S + 1;         // episode length in ctrl steps: the counter restarts with the episode
         const bool fin = lead && done;
         const unsigned m = __ballot_sync(0xffffffffu, fin);
         if (m) {                        // reduce over the warp, then one set of shared-memory atomics per warp
@@ -473,10 +483,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 if (nt) atomicAdd(&sm.stat_f()[2], (float)nt);
             }
         }
-        if (lead) {
-            a.p.ep_ret[e] = fin ? 0.f : er;
-            a.p.ep_len[e] = fin ? 0 : el;
-        }
+        if (lead) a.p.ep_ret[e] = fin ? 0.f : er;
     }
     if (a.auto_reset && active) {
         if (done) {
@@ -518,7 +525,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
                 r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
                 r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
-                r[(a.W >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);   // newest ring slot, BaseRLAviary.py:187
+                const int W4 = a.W >> 2;
+                r[W4 - 1] = make_float4(act[0], act[1], act[2], act[3]);           // newest ring slot, BaseRLAviary.py:187
+                if (a.use_tma && a.tma_edge) { r[3] = edge_lo; r[W4 - 2] = edge_hi; }   // complete the two shared sectors
             } else {
                 float* r = reinterpret_cast<float*>(a.obs_out) + d * a.W;
 #pragma unroll
@@ -587,7 +596,7 @@ reset_kernel(const __grid_constant__ StepArgs<R> a)
             a.p.aux_rpm[d] = M<R>::make4(R(0), R(0), R(0), R(0));
             if (i == 0) {
                 a.p.counter[e] = 0;
-                if (a.p.ep_ret) { a.p.ep_ret[e] = 0.f; a.p.ep_len[e] = 0; }
+                if (a.p.ep_ret) a.p.ep_ret[e] = 0.f;
             }
         } else {
             load_state(a.p, d, s);
