@@ -36,7 +36,7 @@ METRIC = "drone-substeps/sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--sets", type=int, default=8, help="independent env sets rotated to defeat L2 residency")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--tpb", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -131,18 +131,16 @@ class ClockSampler:
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake": 0x80, "sync_boost": 0x10}
         while not self._stop.is_set():
-            try:
-                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+            try:        # every sample between start() and stop() is taken while the timed regions run
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                if util > 0:
-                    self.samples.append(mhz)
-                    for k, bit in names.items():
-                        if rs & bit:
-                            self.reasons.add(k)
+                self.samples.append(mhz)
+                for k, bit in names.items():
+                    if rs & bit:
+                        self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def start(self):
         if self.nv is not None:
@@ -229,10 +227,13 @@ def b200_arm(a):
     K = reps * period
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if graph is not None:           # bring the clocks to their loaded state before sampling starts
+        for _ in range(max(1, reps // 4)):
+            graph.replay()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(reps):
@@ -299,7 +300,8 @@ def b200_arm(a):
         tr = traffic_from_profile()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
-                "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_note": (tr or {}).get("note"),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel<float,LEAN,N=1,VEC>",
                 "kernel_ms_per_launch": per_launch_ms}
         cpu = None

@@ -26,7 +26,8 @@ SYMBOLS = [
     "gpd_version", "gpd_last_error", "gpd_device_count", "gpd_create", "gpd_destroy", "gpd_obs_width",
     "gpd_action_width", "gpd_substeps", "gpd_set_init_poses", "gpd_reset", "gpd_step", "gpd_step_host",
     "gpd_reset_host", "gpd_get_state", "gpd_set_state", "gpd_pid_compute", "gpd_force_ground_effect",
-    "gpd_force_drag", "gpd_force_downwash", "gpd_rollout_pid", "gpd_episode_stats",
+    "gpd_force_drag", "gpd_force_downwash", "gpd_rollout_pid", "gpd_episode_stats", "gpd_grid_size",
+    "gpd_set_timeline_buffer",
 ]
 
 
@@ -148,6 +149,8 @@ def load(path: str | None = None):
     L.gpd_force_downwash.argtypes = [C.c_int, C.c_int, C.POINTER(DroneParamsC), i64, i32, vp, vp, vp]
     L.gpd_rollout_pid.argtypes = [vp, i32, vp, i32, vp, vp, vp]
     L.gpd_episode_stats.argtypes = [vp, C.POINTER(dbl), C.c_int, vp]
+    L.gpd_grid_size.argtypes = [vp]
+    L.gpd_set_timeline_buffer.argtypes = [vp, vp]
     if path is None:
         _lib = L
     return L

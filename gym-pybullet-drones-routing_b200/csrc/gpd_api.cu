@@ -260,6 +260,13 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.tma_bytes = s->tma_bytes;
     a.tma_bytes_box = s->tma_bytes_box;
     a.tma_edge = s->tma_edge;
+    {
+        const char* ev = getenv("GPD_STAGGER_NS");
+        const char* eg = getenv("GPD_STAGGER_GROUPS");
+        a.stagger_ns = ev ? atoi(ev) : 0;
+        a.stagger_groups = eg ? atoi(eg) : 2;
+        if (a.stagger_groups < 1) a.stagger_groups = 1;
+    }
     a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207
@@ -353,9 +360,11 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     s->tma_bytes_box = s->tma_ok ? DPB * (s->B - 1 - 2 * s->tma_edge) * 16 : 0;
     s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128;
     s->lc.smem = (size_t)s->tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
-    {
+    {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
+        // parameter fetch overlap the previous kernel's tail); with a full wave the early-resident CTAs all issue their
+        // loads at the same instant after the wait and the burst costs more than the overlap gains
         const char* ev = getenv("GPD_PDL");
-        s->lc.pdl = ev ? atoi(ev) : 1;
+        s->lc.pdl = ev ? atoi(ev) : (s->lc.grid <= 296 ? 1 : 0);
     }
     if (s->lc.grid > 0x7fffffffLL) { delete s; return fail(GPD_ERR_INVALID, "too many envs for one launch"); }
     int rc = cfg->precision == GPD_F64 ? build_args(s, s->a64) : build_args(s, s->a32);
@@ -594,6 +603,16 @@ int gpd_force_downwash(int device, int precision, const gpd_drone_params* d, int
         CU(launch_downwash<float>(P, num_envs, num_drones, (const float*)pos, (float*)out, (cudaStream_t)stream)); }
     return GPD_OK;
 }
+
+int gpd_set_timeline_buffer(gpd_sim* s, unsigned long long* dev_buf)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    s->a32.timeline = dev_buf;
+    s->a64.timeline = dev_buf;
+    return GPD_OK;
+}
+
+int gpd_grid_size(const gpd_sim* s) { return s ? (int)s->lc.grid : fail(GPD_ERR_INVALID, "null handle"); }
 
 int gpd_rollout_pid(gpd_sim* s, int32_t n_ctrl_steps, const void* waypoints, int32_t n_wp,
                     int32_t* wp_counters, void* action, void* stream)

@@ -29,6 +29,14 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GPD_STAMP(slot) do { if (a.timeline && stamp_lane) a.timeline[(int64_t)blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+
 // Physics-only barrier (named barrier 1): the DMA/copy warp of the block never joins it.
 __device__ __forceinline__ void phys_sync(int nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
 
@@ -259,12 +267,19 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool spec = a.copy_threads > 0;
     const bool run_physics = t < nphys;
 
+    const bool stamp_lane = (t == 0) || (t == nphys);
+    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 0] = gtime();      // 0: CTA start (params fetched)
     pdl_launch_dependents();
     if (a.auto_reset) {
         if (t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
         __syncthreads();
     }
     pdl_wait();                         // everything above touched only parameters and shared memory
+    if (a.stagger_ns > 0) {             // de-phase the CTAs of a single-wave launch: odd groups start their loads later
+        const unsigned g = blockIdx.x % (unsigned)a.stagger_groups;
+        if (g) __nanosleep(g * (unsigned)a.stagger_ns);
+    }
+    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
 
     if (spec && !run_physics) {
         if (VEC && a.use_tma) {
@@ -276,7 +291,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 // whole by the drone's own thread (no partial-sector L2 fills from DRAM).
                 tma_load_2d(smem_raw, &tm_prev, 12 + 4 * (a.tma_edge + 1), (int)row0, &tma_bar);
                 mbar_wait(&tma_bar, 0);
+                if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 5] = gtime();    // 5: history tile landed in smem
                 tma_store_2d(&tm_out, 12 + 4 * a.tma_edge, (int)row0, smem_raw);
+                if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 6] = gtime();    // 6: TMA store has read smem
             }
         } else {
             copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
@@ -295,8 +312,12 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     int32_t cnt = 0;
     float ep_ret0 = 0.f;
     float4 edge_lo = make_float4(0.f, 0.f, 0.f, 0.f), edge_hi = edge_lo;     // old ring slots 1 and B-1 (see the DMA warp)
+    V4<R> tg = M<R>::make4(R(0), R(0), R(0), R(0)), ip0 = tg, iq0 = tg;
+    const bool pre_init = a.auto_reset && !a.init_per_env;      // shared initial pose: fetch it now, off the epilogue's critical path
     if (active) {
         load_state(a.p, d, s);
+        if (!ctrl) tg = a.p.target[i];
+        if (pre_init) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
         if (i == 0) {                   // per-env bookkeeping: loaded here so its DRAM latency hides behind the physics
             cnt = a.p.counter[e];
             if (a.auto_reset) ep_ret0 = a.p.ep_ret[e];
@@ -354,6 +375,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     Forcing<R> F;
     make_forcing(P, rpm, F);
     const R rpm_r[4] = { (R)rpm[0], (R)rpm[1], (R)rpm[2], (R)rpm[3] };
+    if (a.timeline && t == 0 && F.T == F.T) a.timeline[(int64_t)blockIdx.x * 8 + 2] = gtime();   // 2: state + action arrived
 
     // ---- PYB_STEPS_PER_CTRL substeps (BaseAviary.py:343-372), state in registers ----
     R avx = R(0), avy = R(0), avz = R(0);
@@ -397,6 +419,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         }
     }
 
+    if (a.timeline && t == 0 && s.px == s.px) a.timeline[(int64_t)blockIdx.x * 8 + 3] = gtime(); // 3: substeps done
     // ---- _updateAndStoreKinematicInformation (BaseAviary.py:374,509-519) + outputs ----
     R roll, pitch, yaw;
     quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
@@ -404,7 +427,6 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     R rew = R(-1);                      // CtrlAviary.py:144-200: dummy reward/flags
     int term = 0, trunc = 0;
     if (!ctrl) {
-        V4<R> tg = a.p.target[i];
         R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
         R dist = M<R>::sqrt(ex * ex + ey * ey + ez * ez);
         R d2 = dist * dist;
@@ -493,7 +515,14 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 tk[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
                 tk[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
             }
-            init_state(a, d, i, s);     // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
+            if (pre_init) {             // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
+                s.px = ip0.x; s.py = ip0.y; s.pz = ip0.z;
+                s.qx = iq0.x; s.qy = iq0.y; s.qz = iq0.z; s.qw = iq0.w;
+                s.vx = s.vy = s.vz = R(0);
+                s.wx = s.wy = s.wz = R(0);
+            } else {
+                init_state(a, d, i, s);
+            }
             quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
             avx = avy = avz = R(0);
             out_rpm[0] = out_rpm[1] = out_rpm[2] = out_rpm[3] = R(0);       // last_clipped_action zeroed, :468
@@ -537,8 +566,10 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }
     }   // run_physics
 
+    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 4] = gtime();      // 4: physics thread 0 stored everything
     // ---- Ctrl observation tile: coalesced write of the staged state20 rows (contiguous in global memory) ----
     if (ctrl || a.auto_reset) __syncthreads();
+    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 7] = gtime();      // 7: block barrier passed
     if (ctrl) {
         const R* st = sm.stage_r();
         R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;

@@ -193,6 +193,13 @@ int gpd_force_downwash(int device, int precision, const gpd_drone_params* d, int
 int gpd_rollout_pid(gpd_sim* sim, int32_t n_ctrl_steps, const void* waypoints, int32_t n_wp,
                     int32_t* wp_counters, void* action, void* stream);
 
+/* Diagnostics: number of CTAs of a step launch, and an optional device buffer [grid][8] of uint64 that every step
+ * launch fills with per-CTA phase timestamps in ns (%globaltimer): 0 CTA start, 1 previous kernel complete (PDL wait
+ * passed), 2 state+action arrived, 3 substeps done, 4 physics outputs stored, 5 history tile landed in shared memory
+ * (TMA load), 6 TMA store consumed shared memory, 7 block barrier passed. NULL (default) disables it. */
+int gpd_grid_size(const gpd_sim* sim);
+int gpd_set_timeline_buffer(gpd_sim* sim, unsigned long long* dev_buf);
+
 /* Episode statistics kept on the device when auto_reset is on (what SB3's Monitor reports in the
  * single-process reference, examples/learn.py:53-57,142-146). out (host) = { episodes, sum_return, sum_length,
  * sum_return_sq, min_return, max_return, env_steps, terminated_episodes }. Synchronises `stream`.
