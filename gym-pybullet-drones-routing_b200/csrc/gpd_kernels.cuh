@@ -281,8 +281,12 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
 
+    const bool tma_copy = spec && VEC && a.use_tma;
+    if (!ctrl && !tma_copy)             // no TMA for this row shape (A = 3 or 1) or no previous observation: every thread
+        copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
+                          row0, rows, a.W, a.A, a.B, true, t, (int)blockDim.x);   // of the block shares the register copy
     if (spec && !run_physics) {
-        if (VEC && a.use_tma) {
+        if (tma_copy) {
             if (t == nphys) {           // one lane drives the TMA engine: global -> shared -> global, shifted by one slot
                 mbar_init(&tma_bar, 1);
                 mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
@@ -295,9 +299,6 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 tma_store_2d(&tm_out, 12 + 4 * a.tma_edge, (int)row0, smem_raw);
                 if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 6] = gtime();    // 6: TMA store has read smem
             }
-        } else {
-            copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
-                              row0, rows, a.W, a.A, a.B, true, t - nphys, a.copy_threads);
         }
     }
 
@@ -350,11 +351,6 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         }
     }
 
-    // ---- action history of the observation: independent of the physics, issue it now ----
-    if (!ctrl && !spec)
-        copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
-                          row0, rows, a.W, a.A, a.B, true, t, nphys);
-
     // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238) ----
     if (a.action_type == GPD_ACT_RPM) {
 #pragma unroll
@@ -391,7 +387,19 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             const R* pb = nullptr;
             if (a.phy & GPD_PHY_GND) {
                 R roll, pitch, yaw;
-                quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);     // snapshot rpy, :346-347,518
+                if constexpr (M<R>::is_double) {
+                    quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw); // snapshot rpy, :346-347,518
+                } else {
+                    // FP32 throughput mode: the gate |roll|,|pitch| < pi/2 (BaseAviary.py:742) only needs the signs of the
+                    // atan2/asin arguments: |atan2(y,x)| < pi/2 <=> x > 0 (or x = y = 0); |asin(s)| < pi/2 <=> |s| < 1, and
+                    // Bullet's gimbal branch (|s| >= 0.99999) returns pitch = +-pi/2, which fails the gate.
+                    const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
+                    const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
+                    const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
+                    roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
+                    pitch = gimbal ? R(GPD_PI) : R(0);
+                    yaw = R(0);
+                }
                 if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
             }
             if (a.phy & GPD_PHY_DRAG) {                          // :359,366: rpm = last_clipped_action

@@ -239,15 +239,27 @@ __device__ __forceinline__ R downwash_pair(const DevDrone<R>& P, R mx, R my, R m
 {
     R delta_z = oz - mz;                                                                   // :799
     R dx = ox - mx, dy = oy - my;
-    R delta_xy = M<R>::sqrt(dx * dx + dy * dy);                                            // :800
-    if (delta_z > R(0) && delta_xy < R(10)) {                                              // :801
-        R ratio = P.PROP_RADIUS / (R(4) * delta_z);
-        R alpha = P.DW1 * (ratio * ratio);                                                 // :802
-        R beta = P.DW2 * delta_z + P.DW3;                                                  // :803
-        R u = delta_xy / beta;
-        return -alpha * M<R>::exp(R(-.5) * (u * u));                                       // :804
+    if constexpr (M<R>::is_double) {
+        R delta_xy = M<R>::sqrt(dx * dx + dy * dy);                                        // :800
+        if (delta_z > R(0) && delta_xy < R(10)) {                                          // :801
+            R ratio = P.PROP_RADIUS / (R(4) * delta_z);
+            R alpha = P.DW1 * (ratio * ratio);                                             // :802
+            R beta = P.DW2 * delta_z + P.DW3;                                              // :803
+            R u = delta_xy / beta;
+            return -alpha * M<R>::exp(R(-.5) * (u * u));                                   // :804
+        }
+        return R(0);
+    } else {
+        // FP32 throughput mode: the same expression on squared distances with MUFU reciprocals and ex2
+        // (u^2 = dxy^2 / beta^2, so the sqrt of :800 disappears; delta_xy < 10 <=> dxy^2 < 100).
+        const float d2 = dx * dx + dy * dy;
+        const float rz = __fdividef(P.PROP_RADIUS * 0.25f, delta_z);
+        const float beta = fmaf(P.DW2, delta_z, P.DW3);
+        const float ib = __fdividef(1.0f, beta);
+        const float e = exp2f(-0.72134752044448170368f * d2 * (ib * ib));                  // exp(-0.5 u^2)
+        const float f = -P.DW1 * (rz * rz) * e;
+        return (delta_z > 0.f && d2 < 100.f) ? f : 0.f;
     }
-    return R(0);
 }
 
 // One DYN substep, BaseAviary._dynamics (BaseAviary.py:831-874).
