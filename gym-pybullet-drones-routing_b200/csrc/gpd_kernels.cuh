@@ -604,7 +604,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
 // reset: BaseAviary.reset (BaseAviary.py:220-255) for the masked envs + observation of every env.
 // ============================================================================================
 template <typename R, bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(288)
 reset_kernel(const __grid_constant__ StepArgs<R> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

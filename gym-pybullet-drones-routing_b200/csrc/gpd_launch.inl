@@ -57,6 +57,13 @@ template <>
 cudaError_t launch_reset<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
 {
     const bool vec = a.A == 4 && a.env_kind != GPD_ENV_CTRL && (a.W % 4 == 0);
+    static size_t smem_set[2] = { 48 * 1024, 48 * 1024 };
+    if (lc.smem > smem_set[vec]) {
+        cudaError_t e = vec ? cudaFuncSetAttribute(reset_kernel<Real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem)
+                            : cudaFuncSetAttribute(reset_kernel<Real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
+        if (e != cudaSuccess) return e;
+        smem_set[vec] = lc.smem;
+    }
     if (vec) reset_kernel<Real, true><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
     else reset_kernel<Real, false><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
     return cudaGetLastError();

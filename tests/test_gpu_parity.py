@@ -413,3 +413,91 @@ def test_cuda_vec_env_protocol():
     o, r, te, tr = venv.step_tensor(torch.zeros((E, 1, 4), device="cuda"))
     assert o.is_cuda and o.shape == (E, 1, 72) and te.dtype == torch.bool
     venv.close()
+
+
+@pytest.mark.parametrize("desc,kw_over,E,steps", [
+    ("single env, single drone", dict(), 1, 40),
+    ("S=1, B=120: history box wider than a TMA box -> register copy", dict(ctrl_freq=240), 33, 30),
+    ("B=1: ring holds only the newest action", dict(pyb_freq=6, ctrl_freq=3), 65, 12),
+    ("B=2", dict(pyb_freq=20, ctrl_freq=4), 65, 12),
+    ("3 drones, E not a multiple of the envs per block", dict(env_kind="multihover", num_drones=3), 43, 30),
+    ("ONE_D_RPM (A=1, scalar rows)", dict(action_type="one_d_rpm"), 70, 30),
+    ("DYN+DRAG single drone", dict(physics_flags=2), 70, 30),
+    ("DYN+GND+DRAG+DW, 5 drones", dict(env_kind="multihover", num_drones=5, physics_flags=7), 21, 30),
+])
+def test_cuda_f64_edge_shapes_vs_oracle(desc, kw_over, E, steps):
+    """Ragged / extreme shapes: every code path of the step kernel (TMA and register history copy, all block tails)
+    against the oracle in FP64."""
+    rng = np.random.default_rng(abs(hash(desc)) % 2**31)
+    kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    kw.update(kw_over)
+    N = kw["num_drones"]
+    A = {"rpm": 4, "one_d_rpm": 1}[kw["action_type"]]
+    if N > 1:
+        xyz = np.stack([rng.uniform(-.5, .5, (E, N)), rng.uniform(-.5, .5, (E, N)), rng.uniform(0.03, 1.0, (E, N))], -1)
+        kw["init_xyz"], kw["init_rpy"] = xyz, rng.uniform(-.2, .2, (E, N, 3))
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E)
+    obs0 = sim.reset()
+    assert np.max(np.abs(obs0.cpu().numpy() - ref.obs)) <= 1e-6
+    for t in range(steps):
+        a = (0.3 * rng.standard_normal(size=(E, N, A))).astype(np.float32)
+        obs, rew, term, trunc = sim.step(torch.from_numpy(a).cuda())
+        o_ref, r_ref, te_ref, tr_ref = ref.step(a)
+        st, _, cnt = state_np(sim)
+        rs = np.concatenate([ref.state20, ref.rpy_rates], axis=-1)
+        for sl in (S_POS, S_VEL, S_RATES, S_ANGV, S_RPM):
+            assert rel_err(st[..., sl], rs[..., sl]) <= 1e-9, (desc, t, sl)
+        assert np.max(np.abs(obs.cpu().numpy().astype(np.float64) - o_ref) / np.maximum(np.abs(o_ref), 1.0)) <= 1e-6, (desc, t)
+        assert np.array_equal(term.cpu().numpy(), te_ref) and np.array_equal(trunc.cpu().numpy(), tr_ref)
+        assert np.array_equal(cnt, ref.step_counter)
+    sim.close()
+
+
+def test_cuda_ctrl_max_drones_per_env():
+    """N = GPD_MAX_DRONES_PER_ENV (256): one block per env; CtrlAviary state20 observation, DYN+DW, vs the oracle."""
+    rng = np.random.default_rng(77)
+    E, N = 3, 256
+    xyz = np.concatenate([rng.uniform(-3, 3, (E, N, 2)), rng.uniform(0.2, 3, (E, N, 1))], -1)
+    kw = dict(model=DroneModel.CF2X, env_kind="ctrl", action_type="ctrl_rpm", num_drones=N, pyb_freq=240, ctrl_freq=48,
+              physics_flags=4, init_xyz=xyz, init_rpy=np.zeros((E, N, 3)))
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E)
+    sim.reset()
+    hover = load_drone_params(DroneModel.CF2X).HOVER_RPM
+    for t in range(6):
+        a = hover * (1 + 0.02 * rng.uniform(-1, 1, (E, N, 4)))
+        obs, _, _, _ = sim.step(torch.from_numpy(a).cuda())
+        o_ref, _, _, _ = ref.step(a)
+        assert rel_err(obs.cpu().numpy()[..., 0:3], o_ref[..., 0:3]) <= 1e-9
+        assert rel_err(obs.cpu().numpy()[..., 10:13], o_ref[..., 10:13]) <= 1e-8
+    with pytest.raises(Exception):
+        make_sim(dict(kw, num_drones=257, init_xyz=None, init_rpy=None), num_envs=1)
+    sim.close()
+
+
+def test_cuda_masked_reset_with_per_env_poses():
+    """reset(mask) touches only the masked envs, uses each env's own initial pose, keeps the ring (obs history)."""
+    rng = np.random.default_rng(31)
+    E = 150
+    xyz, rpy = _random_init(rng, E, 1)
+    kw = dict(model=DroneModel.CF2P, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=xyz, init_rpy=rpy)
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E)
+    sim.reset()
+    for t in range(20):
+        a = rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)
+        sim.step(torch.from_numpy(a).cuda()); ref.step(a)
+        if t in (5, 11):
+            mask = rng.uniform(size=E) < 0.3
+            o = sim.reset(torch.from_numpy(mask.astype(np.uint8)))
+            o_ref = ref.reset(mask.astype(np.uint8))
+            assert np.max(np.abs(o.cpu().numpy() - o_ref)) <= 1e-6
+            st, _, cnt = state_np(sim)
+            assert np.all(cnt[mask] == 0) and np.all(cnt[~mask] > 0)
+            assert rel_err(st[mask][:, 0, 0:3], xyz[mask][:, 0]) <= 1e-15
+    st, _, _ = state_np(sim)
+    assert rel_err(st[..., S_POS], ref.state20[..., S_POS]) <= 1e-9
+    sim.close()
