@@ -287,7 +287,7 @@ def b200_arm(a):
     e2e_val = world * E * S * a.e2e_steps / e2e_s
     W = env._sim.W
     h2d = E * 4 * 4
-    d2h = E * (W * 4 + 4 + 1 + 1 + 12 * 4)
+    d2h = E * (W * 4 + 4 + 1 + 1)      # obs + reward + terminated + truncated, one packed copy
     clocks = sampler.stop()
 
     if rank == 0:

@@ -70,9 +70,6 @@ struct gpd_sim {
     // host-buffer path (gpd_step_host): device I/O buffers + obs ping-pong, allocated lazily
     void* h_act = nullptr;
     void* h_obs[2] = { nullptr, nullptr };
-    void* h_rew = nullptr;
-    uint8_t* h_term = nullptr;
-    uint8_t* h_trunc = nullptr;
     float* h_tkin = nullptr;
     int h_cur = 0;
     bool h_has_prev = false;
@@ -383,8 +380,8 @@ void gpd_destroy(gpd_sim* s)
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     for (void* p : s->allocs) cudaFree(p);
-    cudaFree(s->h_act); cudaFree(s->h_obs[0]); cudaFree(s->h_obs[1]); cudaFree(s->h_rew);
-    cudaFree(s->h_term); cudaFree(s->h_trunc); cudaFree(s->h_tkin); cudaFree(s->stats_out);
+    cudaFree(s->h_act); cudaFree(s->h_obs[0]); cudaFree(s->h_obs[1]);
+    cudaFree(s->h_tkin); cudaFree(s->stats_out);
     delete s;
 }
 
@@ -453,12 +450,14 @@ static int ensure_host_path(gpd_sim* s)
     const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
     const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
     size_t act_b = (size_t)s->D * s->A * (ctrl ? rs : 4), obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
+    // each ping-pong slot is one packed block [obs | reward | terminated | truncated]: when the caller's host arrays are
+    // laid out the same way (the Python facade allocates them so) the whole result travels in ONE device-to-host copy
+    const size_t E = (size_t)s->cfg.num_envs;
+    const size_t obs_pad = (obs_b + 15) & ~size_t(15);     // keeps the reward block aligned for Real stores
+    const size_t pack_b = obs_pad + E * rs + 2 * E;
     CU(cudaMalloc(&s->h_act, act_b));
-    CU(cudaMalloc(&s->h_obs[0], obs_b));
-    CU(cudaMalloc(&s->h_obs[1], obs_b));
-    CU(cudaMalloc(&s->h_rew, (size_t)s->cfg.num_envs * rs));
-    CU(cudaMalloc((void**)&s->h_term, (size_t)s->cfg.num_envs));
-    CU(cudaMalloc((void**)&s->h_trunc, (size_t)s->cfg.num_envs));
+    CU(cudaMalloc(&s->h_obs[0], pack_b));
+    CU(cudaMalloc(&s->h_obs[1], pack_b));
     CU(cudaMalloc((void**)&s->h_tkin, (size_t)s->D * 12 * sizeof(float)));
     CU(cudaMemset(s->h_tkin, 0, (size_t)s->D * 12 * sizeof(float)));
     return GPD_OK;
@@ -477,14 +476,26 @@ int gpd_step_host(gpd_sim* s, const void* actions, void* obs_out, void* reward,
     size_t act_b = (size_t)s->D * s->A * (ctrl ? rs : 4), obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
     CU(cudaMemcpyAsync(s->h_act, actions, act_b, cudaMemcpyHostToDevice, st));
     int nxt = s->h_cur ^ 1;
-    rc = gpd_step(s, s->h_act, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], s->h_rew, s->h_term, s->h_trunc,
+    const size_t E = (size_t)s->cfg.num_envs;
+    char* pack = (char*)s->h_obs[nxt];
+    const size_t obs_pad = (obs_b + 15) & ~size_t(15);
+    void* d_rew = pack + obs_pad;
+    uint8_t* d_term = (uint8_t*)(pack + obs_pad + E * rs);
+    uint8_t* d_trunc = d_term + E;
+    rc = gpd_step(s, s->h_act, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], d_rew, d_term, d_trunc,
                   terminal_kin ? s->h_tkin : nullptr, stream);
     if (rc) return rc;
     s->h_cur = nxt; s->h_has_prev = true;
-    CU(cudaMemcpyAsync(obs_out, s->h_obs[nxt], obs_b, cudaMemcpyDeviceToHost, st));
-    if (reward) CU(cudaMemcpyAsync(reward, s->h_rew, (size_t)s->cfg.num_envs * rs, cudaMemcpyDeviceToHost, st));
-    if (terminated) CU(cudaMemcpyAsync(terminated, s->h_term, (size_t)s->cfg.num_envs, cudaMemcpyDeviceToHost, st));
-    if (truncated) CU(cudaMemcpyAsync(truncated, s->h_trunc, (size_t)s->cfg.num_envs, cudaMemcpyDeviceToHost, st));
+    const bool packed = reward == (char*)obs_out + obs_pad && (void*)terminated == (char*)reward + E * rs &&
+                        truncated == terminated + E;
+    if (packed) {
+        CU(cudaMemcpyAsync(obs_out, pack, obs_pad + E * rs + 2 * E, cudaMemcpyDeviceToHost, st));
+    } else {
+        CU(cudaMemcpyAsync(obs_out, pack, obs_b, cudaMemcpyDeviceToHost, st));
+        if (reward) CU(cudaMemcpyAsync(reward, d_rew, E * rs, cudaMemcpyDeviceToHost, st));
+        if (terminated) CU(cudaMemcpyAsync(terminated, d_term, E, cudaMemcpyDeviceToHost, st));
+        if (truncated) CU(cudaMemcpyAsync(truncated, d_trunc, E, cudaMemcpyDeviceToHost, st));
+    }
     if (terminal_kin) CU(cudaMemcpyAsync(terminal_kin, s->h_tkin, (size_t)s->D * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return GPD_OK;

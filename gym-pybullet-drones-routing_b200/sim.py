@@ -151,18 +151,33 @@ class BatchedSim:
                                            C.c_void_p(obs.ctypes.data), self._stream()))
         return obs
 
-    def alloc_host_outputs(self, pinned: bool = False):
-        odt = self.np_real if self.is_ctrl else np.float32
-        shapes = [((self.E, self.N, self.W), odt), ((self.E,), self.np_real), ((self.E,), np.uint8), ((self.E,), np.uint8)]
+    def alloc_host_outputs(self, pinned: bool = False, terminal_kin: bool | None = None):
+        """Host result arrays (obs, reward, terminated, truncated, terminal_kin|None) carved out of ONE block laid out
+        [obs | reward | terminated | truncated], so gpd_step_host returns everything in a single device-to-host copy.
+        ``terminal_kin`` (12 floats per drone, needed only to rebuild SB3's terminal_observation) is transferred only
+        when asked for (default: never for plain step(), always for the VecEnv adapter)."""
+        odt = np.dtype(self.np_real if self.is_ctrl else np.float32)
+        rdt = np.dtype(self.np_real)
+        obs_b = self.E * self.N * self.W * odt.itemsize
+        obs_pad = (obs_b + 15) & ~15                      # same padding as gpd_step_host's packed device block
+        rew_b = self.E * rdt.itemsize
+        total = obs_pad + rew_b + 2 * self.E
         if pinned:
-            arrs = [torch.empty(s, dtype=torch.from_numpy(np.empty(0, d)).dtype).pin_memory().numpy() for s, d in shapes]
+            block = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
         else:
-            arrs = [np.empty(s, dtype=d) for s, d in shapes]
+            block = np.empty(total, dtype=np.uint8)
+        obs = block[:obs_b].view(odt).reshape(self.E, self.N, self.W)
+        rew = block[obs_pad:obs_pad + rew_b].view(rdt)
+        term = block[obs_pad + rew_b:obs_pad + rew_b + self.E]
+        trunc = block[obs_pad + rew_b + self.E:]
         tkin = None
-        if self.auto_reset and not self.is_ctrl:
+        if terminal_kin is None:
+            terminal_kin = False
+        if terminal_kin and self.auto_reset and not self.is_ctrl:
             tkin = (torch.empty((self.E, self.N, 12), dtype=torch.float32).pin_memory().numpy() if pinned
                     else np.empty((self.E, self.N, 12), np.float32))
-        return (*arrs, tkin)
+        self._host_block = block
+        return (obs, rew, term, trunc, tkin)
 
     # ------------------------------------------------------------------
     def get_state(self):

@@ -70,7 +70,7 @@ class GpdVecEnv:
     def step_wait(self):
         sim = self.env._sim
         if self.env._host_out is None:
-            self.env._host_out = sim.alloc_host_outputs(pinned=torch.cuda.is_available())
+            self.env._host_out = sim.alloc_host_outputs(pinned=torch.cuda.is_available(), terminal_kin=True)
         obs, rew, term, trunc, tkin = sim.step_host(self._actions, self.env._host_out)
         self.env._state_cache = None
         term_b, trunc_b = term.view(np.bool_), trunc.view(np.bool_)
