@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgpd_b200.so")
 
 GPD_F32, GPD_F64 = 0, 1
-ACT_CODES = {"rpm": 0, "pid": 1, "vel": 2, "one_d_rpm": 3, "one_d_pid": 4, "ctrl_rpm": 5}
+ACT_CODES = {"rpm": 0, "pid": 1, "vel": 2, "one_d_rpm": 3, "one_d_pid": 4, "ctrl_rpm": 5, "ctrl_vel": 6}
 ENV_CODES = {"ctrl": 0, "hover": 1, "multihover": 2}
 MODEL_CODES = {"cf2x": 0, "cf2p": 1, "racer": 2}
 

@@ -102,7 +102,7 @@ static const CUtensorMap* get_tmap(gpd_sim* s, const void* base)
 static int action_width(int act)
 {
     switch (act) {
-    case GPD_ACT_RPM: case GPD_ACT_VEL: case GPD_ACT_CTRL_RPM: return 4;
+    case GPD_ACT_RPM: case GPD_ACT_VEL: case GPD_ACT_CTRL_RPM: case GPD_ACT_CTRL_VEL: return 4;
     case GPD_ACT_PID: return 3;
     case GPD_ACT_ONE_D_RPM: case GPD_ACT_ONE_D_PID: return 1;
     default: return -1;
@@ -301,12 +301,13 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     int A = action_width(cfg->action_type);
     if (A < 0) return fail(GPD_ERR_INVALID, "bad action_type");
     const bool ctrl = cfg->env_kind == GPD_ENV_CTRL;
-    if (ctrl != (cfg->action_type == GPD_ACT_CTRL_RPM))
-        return fail(GPD_ERR_INVALID, "GPD_ACT_CTRL_RPM goes with GPD_ENV_CTRL and only with it");
+    if (ctrl != (cfg->action_type == GPD_ACT_CTRL_RPM || cfg->action_type == GPD_ACT_CTRL_VEL))
+        return fail(GPD_ERR_INVALID, "GPD_ACT_CTRL_RPM / GPD_ACT_CTRL_VEL go with GPD_ENV_CTRL and only with it");
     if (cfg->env_kind == GPD_ENV_HOVER && cfg->num_drones != 1) return fail(GPD_ERR_INVALID, "HoverAviary is single-drone");
     if (cfg->env_kind < GPD_ENV_CTRL || cfg->env_kind > GPD_ENV_MULTIHOVER) return fail(GPD_ERR_INVALID, "bad env_kind");
     if (!ctrl && !cfg->target_pos) return fail(GPD_ERR_INVALID, "target_pos is required for the RL envs");
-    const bool pidfam = cfg->action_type == GPD_ACT_PID || cfg->action_type == GPD_ACT_VEL || cfg->action_type == GPD_ACT_ONE_D_PID;
+    const bool pidfam = cfg->action_type == GPD_ACT_PID || cfg->action_type == GPD_ACT_VEL || cfg->action_type == GPD_ACT_ONE_D_PID ||
+                        cfg->action_type == GPD_ACT_CTRL_VEL;
     if (pidfam && cfg->drone.model == GPD_RACE)
         return fail(GPD_ERR_INVALID, "no controller is available for the specified drone_model");   // BaseRLAviary.py:77-78
     if ((cfg->physics_flags & ~(GPD_PHY_GND | GPD_PHY_DRAG | GPD_PHY_DW)) != 0) return fail(GPD_ERR_INVALID, "bad physics_flags");

@@ -334,6 +334,25 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
             rpm[0] = clip(v.x, R(0), P.MAX_RPM); rpm[1] = clip(v.y, R(0), P.MAX_RPM);
             rpm[2] = clip(v.z, R(0), P.MAX_RPM); rpm[3] = clip(v.w, R(0), P.MAX_RPM);
+        } else if (a.action_type == GPD_ACT_CTRL_VEL) {
+            if constexpr (!LEAN) {                               // VelocityAviary.py:129-170, in the action's own precision
+                V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
+                R n = M<R>::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+                R u0 = R(0), u1 = R(0), u2 = R(0);
+                if (n != R(0)) { u0 = v.x / n; u1 = v.y / n; u2 = v.z / n; }
+                const R sp = a.speed_limit * M<R>::abs(v.w);
+                const R tv[3] = { sp * u0, sp * u1, sp * u2 }, tp[3] = { s.px, s.py, s.pz }, z3[3] = { R(0), R(0), R(0) };
+                R roll, pitch, yaw, st[9], r4[4], pe[3], ye;
+                quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+                const R trpy[3] = { R(0), R(0), yaw };
+#pragma unroll
+                for (int k = 0; k < 9; ++k) st[k] = a.p.pid[(int64_t)k * a.D + d];
+                pid_compute(a.pid, a.ctrl_dt, s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, tp, trpy, tv, z3,
+                            st, r4, pe, ye);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a.p.pid[(int64_t)k * a.D + d] = st[k];
+                rpm[0] = r4[0]; rpm[1] = r4[1]; rpm[2] = r4[2]; rpm[3] = r4[3];
+            }
         } else {
             const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
             if constexpr (VEC) {

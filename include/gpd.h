@@ -47,9 +47,10 @@ typedef enum gpd_precision { GPD_F32 = 0, GPD_F64 = 1 } gpd_precision;
 /* utils/enums.py:35-41 (+ CtrlAviary.py:140 raw RPM with clip to [0, MAX_RPM]) */
 typedef enum gpd_action_type {
     GPD_ACT_RPM = 0, GPD_ACT_PID = 1, GPD_ACT_VEL = 2, GPD_ACT_ONE_D_RPM = 3, GPD_ACT_ONE_D_PID = 4,
-    GPD_ACT_CTRL_RPM = 5
+    GPD_ACT_CTRL_RPM = 5,   /* CtrlAviary: raw RPM, clipped to [0, MAX_RPM] (CtrlAviary.py:140) */
+    GPD_ACT_CTRL_VEL = 6    /* VelocityAviary: (vx, vy, vz, speed fraction) tracked by DSLPIDControl (VelocityAviary.py:129-170) */
 } gpd_action_type;
-/* envs/CtrlAviary.py, envs/HoverAviary.py, envs/MultiHoverAviary.py */
+/* envs/CtrlAviary.py (+ envs/VelocityAviary.py: same observation/reward shape), envs/HoverAviary.py, envs/MultiHoverAviary.py */
 typedef enum gpd_env_kind { GPD_ENV_CTRL = 0, GPD_ENV_HOVER = 1, GPD_ENV_MULTIHOVER = 2 } gpd_env_kind;
 /* DYN-form force models (BaseAviary.py:715-811 recast for Physics.DYN) */
 enum { GPD_PHY_GND = 1, GPD_PHY_DRAG = 2, GPD_PHY_DW = 4 };
@@ -133,7 +134,7 @@ int gpd_reset(gpd_sim* sim, const uint8_t* env_mask, const void* obs_prev, void*
  * PYB_STEPS_PER_CTRL substeps of _dynamics/_integrateQ (BaseAviary.py:815-889) with the optional DYN-form
  * force models, _computeObs (BaseRLAviary.py:307-319 / CtrlAviary.py:117), _computeReward/_computeTerminated/
  * _computeTruncated (HoverAviary.py:68-117, MultiHoverAviary.py:84-130), step_counter += S.
- *   actions   dev [E][N][A]: float32 for the RL envs (the SB3 dtype, BaseRLAviary.py:156); Real for GPD_ACT_CTRL_RPM
+ *   actions   dev [E][N][A]: float32 for the RL envs (the SB3 dtype, BaseRLAviary.py:156); Real for GPD_ACT_CTRL_RPM/_VEL
  *   obs_prev  dev, the observation written by the previous gpd_step/gpd_reset on this handle: the RL observation
  *             carries the action ring (BaseRLAviary.py:317-318), so the shifted history is read from it.
  *             NULL = all-zero ring. Ignored for the Ctrl env. Must not alias obs_out.

@@ -9,7 +9,7 @@ the fixtures it writes are committed, together with this script.
 
 What is recorded (all float64 unless noted; NumPy version stored in every file):
   constants.json        _parseURDFParameters + derived constants + DSLPIDControl gains, per model
-  traj_*.npz            action-replay trajectories: float32 (RL) / float64 (Ctrl) action sequence,
+  traj_*.npz            action-replay trajectories (incl. VelocityAviary): float32 (RL) / float64 (Ctrl) action sequence,
                         state20 + rpy_rates + reward/terminated/truncated at checkpoints,
                         obs rows at a few steps
   pid_calls_*.npz       teacher-forced DSLPIDControl.computeControl call logs
@@ -40,9 +40,10 @@ def _load_reference(ref_root):
         from gym_pybullet_drones.envs.CtrlAviary import CtrlAviary
         from gym_pybullet_drones.envs.HoverAviary import HoverAviary
         from gym_pybullet_drones.envs.MultiHoverAviary import MultiHoverAviary
+        from gym_pybullet_drones.envs.VelocityAviary import VelocityAviary
         from gym_pybullet_drones.utils.enums import ActionType, DroneModel, ObservationType, Physics
     return dict(DSLPIDControl=DSLPIDControl, CtrlAviary=CtrlAviary, HoverAviary=HoverAviary,
-                MultiHoverAviary=MultiHoverAviary, ActionType=ActionType, DroneModel=DroneModel,
+                MultiHoverAviary=MultiHoverAviary, VelocityAviary=VelocityAviary, ActionType=ActionType, DroneModel=DroneModel,
                 ObservationType=ObservationType, Physics=Physics)
 
 
@@ -180,6 +181,24 @@ def gen_traj(R, out):
         np.savez_compressed(os.path.join(out, f"traj_{name}.npz"), actions=acts, kind="ctrl", env="CtrlAviary",
                             model=model.value, ctrl_freq=freq, pyb_freq=240, num_drones=n, act_type="ctrl_rpm",
                             init_xyz=xyz, init_rpy=rpy, numpy=np.__version__, **rec)
+
+
+def gen_velocity(R, out):
+    """VelocityAviary (envs/VelocityAviary.py) on Physics.DYN: float64 velocity commands, closed loop -> short horizon."""
+    P, DM = R["Physics"], R["DroneModel"]
+    rng = np.random.default_rng(2100)
+    n, steps = 2, 24
+    xyz = rng.uniform([-1, -1, 0.3], [1, 1, 1.2], size=(n, 3))
+    rpy = np.zeros((n, 3)); rpy[:, 2] = rng.uniform(-.5, .5, n)
+    with quiet():
+        env = R["VelocityAviary"](drone_model=DM.CF2P, num_drones=n, initial_xyzs=xyz, initial_rpys=rpy, physics=P.DYN,
+                                  pyb_freq=240, ctrl_freq=48)
+    acts = np.concatenate([rng.uniform(-1, 1, size=(steps, n, 3)), rng.uniform(0, 1, size=(steps, n, 1))], axis=2)
+    acts[3, 0, :3] = 0.0            # zero direction -> zero unit vector branch (VelocityAviary.py:151-154)
+    rec = replay(env, acts, ckpt_every=1, full_first=steps, obs_steps=set(range(steps)))
+    np.savez_compressed(os.path.join(out, "traj_velocity2_cf2p_48.npz"), actions=acts, kind="ctrl_vel", env="VelocityAviary",
+                        model="cf2p", ctrl_freq=48, pyb_freq=240, num_drones=n, act_type="ctrl_vel", init_xyz=xyz,
+                        init_rpy=rpy, numpy=np.__version__, **rec)
 
 
 def gen_pid(R, out):
@@ -417,15 +436,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,velocity,pid,forces,composite,reset")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     R = _load_reference(a.ref)
-    gen_constants(R, a.out)
-    gen_traj(R, a.out)
-    gen_pid(R, a.out)
-    gen_forces(R, a.out)
-    gen_composite(R, a.out)
-    gen_reset_quirks(R, a.out)
+    gens = dict(constants=gen_constants, traj=gen_traj, velocity=gen_velocity, pid=gen_pid, forces=gen_forces,
+                composite=gen_composite, reset=gen_reset_quirks)
+    for name, fn in gens.items():
+        if not a.only or name in a.only.split(","):
+            fn(R, a.out)
     total = sum(os.path.getsize(os.path.join(a.out, f)) for f in os.listdir(a.out))
     print(f"wrote {len(os.listdir(a.out))} files, {total / 1e6:.2f} MB to {a.out}")
 

@@ -313,7 +313,7 @@ void orc_pid_compute(const orc_pid* c, double dt, const double cur_pos[3], const
 int orc_action_width(int action_type)                                           /* BaseRLAviary.py:140-145 */
 {
     switch (action_type) {
-    case ORC_ACT_RPM: case ORC_ACT_VEL: case ORC_ACT_CTRL_RPM: return 4;
+    case ORC_ACT_RPM: case ORC_ACT_VEL: case ORC_ACT_CTRL_RPM: case ORC_ACT_CTRL_VEL: return 4;
     case ORC_ACT_PID: return 3;
     case ORC_ACT_ONE_D_RPM: case ORC_ACT_ONE_D_PID: return 1;
     default: return -1;
@@ -368,6 +368,17 @@ static void step_one_env(const orc_env_cfg* cfg, double* st, double* rr, double*
         if (cfg->action_type == ORC_ACT_CTRL_RPM) {                      /* CtrlAviary.py:140 */
             const double* a = (const double*)act_env + 4 * i;
             for (int k = 0; k < 4; ++k) r[k] = clipd(a[k], 0, d->MAX_RPM);
+            continue;
+        }
+        if (cfg->action_type == ORC_ACT_CTRL_VEL) {                      /* VelocityAviary.py:148-169 (float64 action) */
+            const double* a = (const double*)act_env + 4 * i;
+            double n = norm3(a), u[3] = { 0, 0, 0 };
+            if (n != 0) { u[0] = a[0] / n; u[1] = a[1] / n; u[2] = a[2] / n; }
+            double sp = cfg->speed_limit * fabs(a[3]);
+            double tv[3] = { sp * u[0], sp * u[1], sp * u[2] };
+            double trpy[3] = { 0, 0, s[S_RPY + 2] }, zero[3] = { 0, 0, 0 };
+            orc_pid_compute(&cfg->pid, ctrl_dt, s + S_POS, s + S_QUAT, s + S_VEL, s + S_POS, trpy, tv, zero,
+                            ps + 9 * i, r, NULL, NULL);
             continue;
         }
         const float* a = (const float*)act_env + A * i;
@@ -490,7 +501,7 @@ static void* step_range(void* arg)
     const orc_env_cfg* cfg = j->cfg;
     int N = cfg->num_drones, A = orc_action_width(cfg->action_type), B = cfg->action_buffer_size;
     int is_ctrl = cfg->env_kind == ORC_ENV_CTRL;
-    size_t act_stride = (size_t)N * A * (cfg->action_type == ORC_ACT_CTRL_RPM ? sizeof(double) : sizeof(float));
+    size_t act_stride = (size_t)N * A * ((cfg->action_type == ORC_ACT_CTRL_RPM || cfg->action_type == ORC_ACT_CTRL_VEL) ? sizeof(double) : sizeof(float));
     size_t obs_stride = is_ctrl ? (size_t)N * 20 * sizeof(double) : (size_t)N * (12 + A * B) * sizeof(float);
     double* scratch = (double*)malloc(sizeof(double) * 7 * (size_t)N);
     for (int64_t e = j->e0; e < j->e1; ++e) {

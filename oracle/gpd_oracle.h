@@ -30,7 +30,8 @@ extern "C" {
 enum { ORC_CF2X = 0, ORC_CF2P = 1, ORC_RACE = 2 };                       /* utils/enums.py:3-8  */
 enum { ORC_ACT_RPM = 0, ORC_ACT_PID = 1, ORC_ACT_VEL = 2,
        ORC_ACT_ONE_D_RPM = 3, ORC_ACT_ONE_D_PID = 4,                     /* utils/enums.py:35-41 */
-       ORC_ACT_CTRL_RPM = 5 };                                           /* envs/CtrlAviary.py:140 */
+       ORC_ACT_CTRL_RPM = 5,                                             /* envs/CtrlAviary.py:140 */
+       ORC_ACT_CTRL_VEL = 6 };                                           /* envs/VelocityAviary.py:129-170 */
 enum { ORC_ENV_CTRL = 0, ORC_ENV_HOVER = 1, ORC_ENV_MULTIHOVER = 2 };
 enum { ORC_PHY_GND = 1, ORC_PHY_DRAG = 2, ORC_PHY_DW = 4 };              /* DYN-form composites (build-defined) */
 
@@ -119,7 +120,7 @@ void orc_calculate_next_step(const double cur[3], const double dest[3], double s
  *   pid_state [E][N][9]   (NULL unless a PID-family action type)
  *   ring      [E][N][B][A] float32, oldest -> newest                          (BaseRLAviary.py:66-67,187)
  *   step_counter [E] int32                                                    (BaseAviary.py:460,382)
- *   actions   [E][N][A]: float32 for RL envs (SB3 dtype, BaseRLAviary.py:156), double for ORC_ACT_CTRL_RPM
+ *   actions   [E][N][A]: float32 for RL envs (SB3 dtype, BaseRLAviary.py:156), double for ORC_ACT_CTRL_RPM/_VEL
  *   target_pos [N][3]  (HoverAviary.py:51, MultiHoverAviary.py:71)
  *   obs: RL envs float32 [E][N][12+A*B] (BaseRLAviary.py:307-319); Ctrl env double [E][N][20] (CtrlAviary.py:117)
  *   reward [E] double, terminated/truncated [E] uint8

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libgpd_oracle.so")
 
-ACT = {"rpm": 0, "pid": 1, "vel": 2, "one_d_rpm": 3, "one_d_pid": 4, "ctrl_rpm": 5}
+ACT = {"rpm": 0, "pid": 1, "vel": 2, "one_d_rpm": 3, "one_d_pid": 4, "ctrl_rpm": 5, "ctrl_vel": 6}
 ENV = {"ctrl": 0, "hover": 1, "multihover": 2}
 MODEL = {"cf2x": 0, "cf2p": 1, "racer": 2}
 PHY_GND, PHY_DRAG, PHY_DW = 1, 2, 4

@@ -54,7 +54,7 @@ def angle_err(a, ref):
 def case_setup(g):
     """kwargs describing the env of a golden trajectory file."""
     model = DroneModel(str(g["model"]))
-    env = {"HoverAviary": "hover", "MultiHoverAviary": "multihover", "CtrlAviary": "ctrl"}[str(g["env"])]
+    env = {"HoverAviary": "hover", "MultiHoverAviary": "multihover", "CtrlAviary": "ctrl", "VelocityAviary": "ctrl"}[str(g["env"])]
     kw = dict(model=model, env_kind=env, action_type=str(g["act_type"]), num_drones=int(g["num_drones"]),
               pyb_freq=int(g["pyb_freq"]), ctrl_freq=int(g["ctrl_freq"]),
               physics_flags=int(g["flags"]) if "flags" in g.files else 0,
@@ -79,7 +79,7 @@ def default_targets(kw):
 def make_oracle(kw, num_envs=1):
     from oracle import oracle as orc
     dp = load_drone_params(kw["model"])
-    pid = default_pid_params(DroneModel.CF2X) if kw["action_type"] in ("pid", "vel", "one_d_pid") else None
+    pid = default_pid_params(DroneModel.CF2X) if kw["action_type"] in ("pid", "vel", "one_d_pid", "ctrl_vel") else None
     return orc.OracleSim(dp, num_envs, num_drones=kw["num_drones"], env_kind=kw["env_kind"],
                          action_type=kw["action_type"], pyb_freq=kw["pyb_freq"], ctrl_freq=kw["ctrl_freq"],
                          physics_flags=kw["physics_flags"], pid_params=pid, init_xyz=kw["init_xyz"],

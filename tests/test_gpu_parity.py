@@ -46,6 +46,14 @@ def test_cuda_f64_replays_reference_trajectory(name):
     obs = sim.reset()
     assert np.max(np.abs(obs.double().cpu().numpy()[1] - g["obs0"])) <= 1e-7 * (tol / 1e-9)
     adt = torch.float64 if kw["env_kind"] == "ctrl" else torch.float32
+    if kw["action_type"] == "ctrl_vel":
+        from gpd_b200.envs import VelocityAviary          # façade smoke: same library path, reference class name
+        ve = VelocityAviary(drone_model=kw["model"], num_drones=kw["num_drones"], initial_xyzs=kw["init_xyz"],
+                            initial_rpys=kw["init_rpy"], pyb_freq=240, ctrl_freq=kw["ctrl_freq"], num_envs=2, precision="f64")
+        assert ve.action_space.shape == (kw["num_drones"], 4) and abs(ve.SPEED_LIMIT - 0.25) < 1e-12
+        o, r, te, tr, _ = ve.step(torch.as_tensor(acts[0][None].repeat(2, 0)).cuda())
+        assert o.shape == (2, kw["num_drones"], 20) and float(r[0]) == -1.0 and not bool(te[0])
+        ve.close()
     dev_acts = torch.as_tensor(np.repeat(acts[:, None], E, axis=1), dtype=adt).cuda()
     for t in range(acts.shape[0]):
         obs, rew, term, trunc = sim.step(dev_acts[t])
