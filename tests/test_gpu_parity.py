@@ -509,3 +509,38 @@ def test_cuda_masked_reset_with_per_env_poses():
     st, _, _ = state_np(sim)
     assert rel_err(st[..., S_POS], ref.state20[..., S_POS]) <= 1e-9
     sim.close()
+
+
+def test_cuda_graphed_rollout_matches_eager_stepping():
+    """policy + env.step captured in one CUDA graph == the same loop stepped eagerly (bit-exact)."""
+    from gpd_b200.envs import HoverAviary
+    from gpd_b200.rollout import GraphedRollout
+    torch.manual_seed(0)
+    E, T = 200, 6
+    W1 = (0.05 * torch.randn(72, 32)).cuda()
+    W2 = (0.5 * torch.randn(32, 4)).cuda()
+
+    def policy(obs):
+        return torch.tanh(torch.tanh(obs.reshape(obs.shape[0], -1) @ W1) @ W2).reshape(obs.shape[0], 1, 4)
+
+    env_g = HoverAviary(num_envs=E, auto_reset=True, precision="f32")
+    env_e = HoverAviary(num_envs=E, auto_reset=True, precision="f32")
+    env_e.reset()
+    for _ in range(2 * T):                     # the collector's two warm-up rollouts advance the env: mirror them
+        o = env_e._sim.obs
+        env_e._sim.step(policy(o))
+    ro = GraphedRollout(env_g, policy, T)      # capture itself does not execute
+    for rep in range(2):
+        obs, act, rew, term, trunc = ro.run()
+        torch.cuda.synchronize()
+        for t in range(T):
+            o = env_e._sim.obs
+            assert torch.equal(obs[t], o)
+            a = policy(o)
+            o2, r2, te2, tr2 = env_e._sim.step(a)
+            assert torch.equal(act[t], a) and torch.equal(rew[t], r2)
+            assert torch.equal(term[t], te2.view(torch.bool)) and torch.equal(trunc[t], tr2.view(torch.bool))
+        assert torch.equal(obs[T], env_e._sim.obs)
+    with pytest.raises(ValueError):
+        GraphedRollout(env_g, policy, 3)
+    env_g.close(); env_e.close()
