@@ -17,6 +17,7 @@ What is recorded (all float64 unless noted; NumPy version stored in every file):
   composite_*.npz       DYN-form composite (build-defined injection of the reference's own force
                         values; NOT a reference mode — SURVEY §8a)
   reset_quirks.npz      ring/controller survival across reset(), truncation clock
+  logger.npz            utils/Logger.py arrays and CSV texts for a small random log
 """
 import argparse
 import contextlib
@@ -199,6 +200,35 @@ def gen_velocity(R, out):
     np.savez_compressed(os.path.join(out, "traj_velocity2_cf2p_48.npz"), actions=acts, kind="ctrl_vel", env="VelocityAviary",
                         model="cf2p", ctrl_freq=48, pyb_freq=240, num_drones=n, act_type="ctrl_vel", init_xyz=xyz,
                         init_rpy=rpy, numpy=np.__version__, **rec)
+
+
+def gen_logger(R, out):
+    """Reference utils/Logger.py on a small random log: arrays + the text of a few CSV files."""
+    import glob
+    import tempfile
+    with quiet():
+        from gym_pybullet_drones.utils.Logger import Logger
+    rng = np.random.default_rng(7000)
+    n, T, hz = 2, 6, 48
+    states = rng.uniform(-1, 1, size=(T, n, 20))
+    states[..., 16:20] = rng.uniform(9000, 20000, size=(T, n, 4))
+    controls = rng.uniform(-1, 1, size=(T, n, 12))
+    with tempfile.TemporaryDirectory() as tmp:
+        lg = Logger(logging_freq_hz=hz, output_folder=tmp, num_drones=n)
+        for t in range(T):
+            for j in range(n):
+                lg.log(drone=j, timestamp=t / hz, state=states[t, j], control=controls[t, j])
+        lg.save()
+        lg.save_as_csv("kat")
+        npy = glob.glob(os.path.join(tmp, "save-flight-*.npy"))[0]
+        z = np.load(npy)
+        csv_dir = [d for d in glob.glob(os.path.join(tmp, "save-flight-kat-*")) if os.path.isdir(d)][0]
+        names = sorted(os.listdir(csv_dir))
+        texts = {k: open(os.path.join(csv_dir, k)).read() for k in ["z0.csv", "rr1.csv", "pwm2-0.csv", "wy1.csv", "ya0.csv"]}
+        np.savez_compressed(os.path.join(out, "logger.npz"), in_states=states, in_controls=controls, hz=hz,
+                            timestamps=z["timestamps"], states=z["states"], controls=z["controls"],
+                            csv_names=np.array(names), csv_keys=np.array(list(texts)), csv_texts=np.array(list(texts.values())),
+                            numpy=np.__version__)
 
 
 def gen_pid(R, out):
@@ -436,12 +466,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,velocity,pid,forces,composite,reset")
+    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,velocity,pid,forces,composite,reset,logger")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     R = _load_reference(a.ref)
     gens = dict(constants=gen_constants, traj=gen_traj, velocity=gen_velocity, pid=gen_pid, forces=gen_forces,
-                composite=gen_composite, reset=gen_reset_quirks)
+                composite=gen_composite, reset=gen_reset_quirks, logger=gen_logger)
     for name, fn in gens.items():
         if not a.only or name in a.only.split(","):
             fn(R, a.out)
