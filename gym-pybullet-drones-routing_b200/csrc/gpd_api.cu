@@ -90,7 +90,8 @@ static const CUtensorMap* get_tmap(gpd_sim* s, const void* base)
     CUtensorMap tm;
     cuuint64_t gdim[2] = { (cuuint64_t)s->W, (cuuint64_t)s->D };
     cuuint64_t gstr[1] = { (cuuint64_t)s->W * 4 };
-    cuuint32_t box[2] = { (cuuint32_t)((s->B - 1 - 2 * s->tma_edge) * 4), (cuuint32_t)s->dpb };
+    // A = 4: the shifted slots only; A < 4: the whole ring (the shift happens in shared memory)
+    cuuint32_t box[2] = { (cuuint32_t)(s->A == 4 ? (s->B - 1 - 2 * s->tma_edge) * 4 : s->A * s->B), (cuuint32_t)s->dpb };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -342,20 +343,21 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     s->lc.threads = P + copy;
     s->dpb = DPB;
     s->lc.grid = (cfg->num_envs + EPB - 1) / EPB;
-    s->tma_ok = !ctrl && A == 4 && s->W % 4 == 0 && s->B >= 2 && (s->B - 1) * 4 <= 256 && DPB <= 256 && get_encode_fn() != nullptr;
+    s->tma_ok = !ctrl && s->W % 4 == 0 && s->B >= 2 && DPB <= 256 && get_encode_fn() != nullptr &&
+                (A == 4 ? (s->B - 1) * 4 <= 256 : ((A * s->B) % 4 == 0 && A * s->B <= 256));
     {
         const char* ev = getenv("GPD_TMA");
         if (ev && atoi(ev) == 0) s->tma_ok = false;
     }
     // whole-sector split of the row between the drone's thread and TMA: pays off once the launch is DRAM-bound; below
     // ~256k drones the launch is latency-bound and the two extra strided loads per thread cost more than the fills
-    s->tma_edge = (s->tma_ok && (s->W / 4) % 2 == 0 && s->B >= 4 && s->D >= 262144) ? 1 : 0;
+    s->tma_edge = (s->tma_ok && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4 && s->D >= 262144) ? 1 : 0;
     {
         const char* ev = getenv("GPD_TMA_EDGE");
         if (ev && atoi(ev) == 0) s->tma_edge = 0;
-        if (ev && atoi(ev) == 1 && s->tma_ok && (s->W / 4) % 2 == 0 && s->B >= 4) s->tma_edge = 1;
+        if (ev && atoi(ev) == 1 && s->tma_ok && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4) s->tma_edge = 1;
     }
-    s->tma_bytes_box = s->tma_ok ? DPB * (s->B - 1 - 2 * s->tma_edge) * 16 : 0;
+    s->tma_bytes_box = !s->tma_ok ? 0 : (A == 4 ? DPB * (s->B - 1 - 2 * s->tma_edge) * 16 : DPB * A * s->B * 4);
     s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128;
     s->lc.smem = (size_t)s->tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the

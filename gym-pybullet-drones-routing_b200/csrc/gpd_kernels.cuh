@@ -103,6 +103,38 @@ __device__ __forceinline__ float ordered_to_float(int i)
     return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
 }
 
+// History write-out for A = 1..3 when the rows are still 16-byte granular (e.g. ActionType.PID at 48 Hz, W = 84): the whole
+// old ring of the tile was TMA-loaded into shared memory (tile[row][A*B floats]); every aligned output float4 is funnelled
+// from two aligned shared-memory float4s (shift by A floats), the last A floats of a row come from this step's action.
+template <int A>
+__device__ __forceinline__ void write_shifted_from_smem(const float4* __restrict__ tile, float* __restrict__ out,
+                                                        const float* __restrict__ act, int64_t row0, int rows, int W, int B,
+                                                        int ct, int CT)
+{
+    const int W4 = W >> 2, H4 = (A * B) >> 2, keep = A * (B - 1);
+    const float* actb = act + row0 * A;
+    float4* out4 = reinterpret_cast<float4*>(out) + row0 * W4 + 3;
+    const int total = rows * H4;
+    for (int idx = ct; idx < total; idx += CT) {
+        const int row = idx / H4, k = idx - row * H4;
+        const float4 lo = tile[row * H4 + k];
+        const float4 hi = (k + 1 < H4) ? tile[row * H4 + k + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v;
+        if (A == 1) v = make_float4(lo.y, lo.z, lo.w, hi.x);
+        else if (A == 2) v = make_float4(lo.z, lo.w, hi.x, hi.y);
+        else v = make_float4(lo.w, hi.x, hi.y, hi.z);
+        const int c = 4 * k;
+        if (c + 3 >= keep) {
+            const float* ar = actb + row * A;
+            if (c + 0 >= keep) v.x = __ldg(ar + (c + 0 - keep));
+            if (c + 1 >= keep) v.y = __ldg(ar + (c + 1 - keep));
+            if (c + 2 >= keep) v.z = __ldg(ar + (c + 2 - keep));
+            if (c + 3 >= keep) v.w = __ldg(ar + (c + 3 - keep));
+        }
+        out4[row * W4 + k] = v;
+    }
+}
+
 // History part of the observation tile: out[row][12 + c] = prev[row][12 + c + A] (c < A*(B-1)),
 // newest entry = this step's action (BaseRLAviary.py:187, deque(maxlen=B)).  shift = false for reset (ring survives).
 // Executed by CT "copier" threads (index ct): either the whole block or, warp-specialised, its upper half.
@@ -243,7 +275,7 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
 //   VEC   : A == 4 (observation rows are float4-granular)
 // ============================================================================================
 template <typename R, bool LEAN, bool MULTI, bool VEC>
-__global__ void __launch_bounds__(MULTI ? 288 : 160, MULTI ? 1 : (sizeof(R) == 4 ? 6 : 2))
+__global__ void __launch_bounds__(MULTI ? 288 : 160, MULTI ? 1 : (sizeof(R) == 4 ? (LEAN ? 6 : 4) : 2))
 step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUtensorMap tm_prev,
             const __grid_constant__ CUtensorMap tm_out)
 {
@@ -281,12 +313,26 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
 
-    const bool tma_copy = spec && VEC && a.use_tma;
+    const bool tma_copy = spec && a.use_tma;
     if (!ctrl && !tma_copy)             // no TMA for this row shape (A = 3 or 1) or no previous observation: every thread
         copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
                           row0, rows, a.W, a.A, a.B, true, t, (int)blockDim.x);   // of the block shares the register copy
     if (spec && !run_physics) {
-        if (tma_copy) {
+        if (tma_copy && !VEC) {         // A = 1..3: TMA load of the whole old ring, shifted write-out by the 32 lanes
+            if (t == nphys) {
+                mbar_init(&tma_bar, 1);
+                mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
+                tma_load_2d(smem_raw, &tm_prev, 12, (int)row0, &tma_bar);
+            }
+            __syncwarp();
+            mbar_wait(&tma_bar, 0);
+            const float4* tile = reinterpret_cast<const float4*>(smem_raw);
+            float* o = reinterpret_cast<float*>(a.obs_out);
+            const float* ac = reinterpret_cast<const float*>(a.actions);
+            if (a.A == 3) write_shifted_from_smem<3>(tile, o, ac, row0, rows, a.W, a.B, t - nphys, a.copy_threads);
+            else if (a.A == 2) write_shifted_from_smem<2>(tile, o, ac, row0, rows, a.W, a.B, t - nphys, a.copy_threads);
+            else write_shifted_from_smem<1>(tile, o, ac, row0, rows, a.W, a.B, t - nphys, a.copy_threads);
+        } else if (tma_copy) {
             if (t == nphys) {           // one lane drives the TMA engine: global -> shared -> global, shifted by one slot
                 mbar_init(&tma_bar, 1);
                 mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
