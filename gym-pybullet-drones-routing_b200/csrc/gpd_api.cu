@@ -77,27 +77,29 @@ struct gpd_sim {
     // TMA: one tensor map per observation buffer the caller has passed (2-D [D rows][W floats], box [DPB][(B-1)*4])
     bool tma_ok = false;
     int tma_bytes = 0, tma_bytes_box = 0, tma_edge = 0;
-    std::unordered_map<const void*, CUtensorMap> tmaps;
+    std::unordered_map<const void*, CUtensorMap> tmaps, tmaps_edge;
+    int tma_edge_bytes = 0;
 };
 
-static const CUtensorMap* get_tmap(gpd_sim* s, const void* base)
+static const CUtensorMap* get_tmap(gpd_sim* s, const void* base, bool edge = false)
 {
-    auto it = s->tmaps.find(base);
-    if (it != s->tmaps.end()) return &it->second;
+    auto& cache = edge ? s->tmaps_edge : s->tmaps;
+    auto it = cache.find(base);
+    if (it != cache.end()) return &it->second;
     encode_tiled_fn enc = get_encode_fn();
     if (!enc || ((uintptr_t)base & 15)) return nullptr;
-    if (s->tmaps.size() > 64) s->tmaps.clear();
+    if (cache.size() > 64) cache.clear();
     CUtensorMap tm;
     cuuint64_t gdim[2] = { (cuuint64_t)s->W, (cuuint64_t)s->D };
     cuuint64_t gstr[1] = { (cuuint64_t)s->W * 4 };
     // A = 4: the shifted slots only; A < 4: the whole ring (the shift happens in shared memory)
-    cuuint32_t box[2] = { (cuuint32_t)(s->A == 4 ? (s->B - 1 - 2 * s->tma_edge) * 4 : s->A * s->B), (cuuint32_t)s->dpb };
+    cuuint32_t box[2] = { (cuuint32_t)(edge ? 4 : (s->A == 4 ? (s->B - 1 - 2 * s->tma_edge) * 4 : s->A * s->B)), (cuuint32_t)s->dpb };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return nullptr;
-    return &s->tmaps.emplace(base, tm).first->second;
+    return &cache.emplace(base, tm).first->second;
 }
 
 static int action_width(int act)
@@ -258,6 +260,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.tma_bytes = s->tma_bytes;
     a.tma_bytes_box = s->tma_bytes_box;
     a.tma_edge = s->tma_edge;
+    a.tma_edge_bytes = s->tma_edge_bytes;
     {
         const char* ev = getenv("GPD_STAGGER_NS");
         const char* eg = getenv("GPD_STAGGER_GROUPS");
@@ -349,8 +352,9 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         const char* ev = getenv("GPD_TMA");
         if (ev && atoi(ev) == 0) s->tma_ok = false;
     }
-    // whole-sector split of the row between the drone's thread and TMA: pays off once the launch is DRAM-bound; below
-    // ~256k drones the launch is latency-bound and the two extra strided loads per thread cost more than the fills
+    // whole-sector split of the row between the drone's thread and TMA (the two old slots the thread needs arrive through
+    // two extra 16-byte-wide TMA boxes): +10 % at >= 1 M drones (DRAM-bound), -2 % below ~256k drones (latency-bound: the
+    // physics threads then wait on the mbarrier and one more block barrier)
     s->tma_edge = (s->tma_ok && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4 && s->D >= 262144) ? 1 : 0;
     {
         const char* ev = getenv("GPD_TMA_EDGE");
@@ -358,7 +362,8 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         if (ev && atoi(ev) == 1 && s->tma_ok && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4) s->tma_edge = 1;
     }
     s->tma_bytes_box = !s->tma_ok ? 0 : (A == 4 ? DPB * (s->B - 1 - 2 * s->tma_edge) * 16 : DPB * A * s->B * 4);
-    s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128;
+    s->tma_edge_bytes = s->tma_edge ? (DPB * 16 + 127) / 128 * 128 : 0;
+    s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128 + 2 * s->tma_edge_bytes;
     s->lc.smem = (size_t)s->tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
         // parameter fetch overlap the previous kernel's tail); with a full wave the early-resident CTAs all issue their
@@ -427,22 +432,24 @@ int gpd_step(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_ou
     cudaStream_t st = (cudaStream_t)stream;
     const CUtensorMap* tp = nullptr;
     const CUtensorMap* to = nullptr;
+    const CUtensorMap* te = nullptr;
     if (s->tma_ok && obs_prev) {
         tp = get_tmap(s, obs_prev);
         to = get_tmap(s, obs_out);
         if (tp) tp = get_tmap(s, obs_prev);     // re-fetch: the second insertion may have rehashed the table
+        if (s->tma_edge) te = get_tmap(s, obs_prev, true);
     }
-    const int use_tma = (tp && to) ? 1 : 0;
+    const int use_tma = (tp && to && (te || !s->tma_edge)) ? 1 : 0;
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        CU(launch_step<double>(a, s->lc, tp, to, st));
+        CU(launch_step<double>(a, s->lc, tp, to, te, st));
     } else {
         StepArgs<float> a = s->a32;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        CU(launch_step<float>(a, s->lc, tp, to, st));
+        CU(launch_step<float>(a, s->lc, tp, to, te, st));
     }
     return GPD_OK;
 }

@@ -83,6 +83,7 @@ struct StepArgs {
     int32_t tma_bytes;      // shared-memory bytes reserved for the TMA tile (multiple of 128)
     int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1-2*tma_edge) * 16
     int32_t stagger_ns, stagger_groups;   // experimental: delay CTA group g by g*stagger_ns after the PDL wait
+    int32_t tma_edge_bytes; // shared-memory bytes of one edge box (DPB*16 rounded up to 128)
     int32_t tma_edge;       // 1: rows are 32-byte aligned, the box skips the first and last shifted slot (written by the drone's thread)
     R dt, ctrl_dt, speed_limit;
     const void* actions;
@@ -109,7 +110,7 @@ struct LaunchCfg {
 
 // implemented once per precision in gpd_f32.cu / gpd_f64.cu
 template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
-                                              const CUtensorMap* tm_out, cudaStream_t st);
+                                              const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st);
 template <typename R> cudaError_t launch_reset(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
 template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, R* state20, R* rpy_rates, R* pid_state,
                                                    int32_t* counter, cudaStream_t st);

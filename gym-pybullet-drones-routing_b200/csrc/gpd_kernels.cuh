@@ -277,7 +277,7 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
 template <typename R, bool LEAN, bool MULTI, bool VEC>
 __global__ void __launch_bounds__(MULTI ? 288 : 160, MULTI ? 1 : (sizeof(R) == 4 ? (LEAN ? 6 : 4) : 2))
 step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUtensorMap tm_prev,
-            const __grid_constant__ CUtensorMap tm_out)
+            const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_edge)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t tma_bar;
@@ -302,10 +302,11 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool stamp_lane = (t == 0) || (t == nphys);
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 0] = gtime();      // 0: CTA start (params fetched)
     pdl_launch_dependents();
-    if (a.auto_reset) {
-        if (t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
-        __syncthreads();
-    }
+    const bool tma_copy = spec && a.use_tma;
+    const bool edge_smem = tma_copy && VEC && a.tma_edge;       // physics threads read the two edge slots from shared memory
+    if (tma_copy && t == nphys) mbar_init(&tma_bar, 1);
+    if (a.auto_reset && t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
+    if (a.auto_reset || edge_smem) __syncthreads();
     pdl_wait();                         // everything above touched only parameters and shared memory
     if (a.stagger_ns > 0) {             // de-phase the CTAs of a single-wave launch: odd groups start their loads later
         const unsigned g = blockIdx.x % (unsigned)a.stagger_groups;
@@ -313,14 +314,12 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
 
-    const bool tma_copy = spec && a.use_tma;
     if (!ctrl && !tma_copy)             // no TMA for this row shape (A = 3 or 1) or no previous observation: every thread
         copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
                           row0, rows, a.W, a.A, a.B, true, t, (int)blockDim.x);   // of the block shares the register copy
     if (spec && !run_physics) {
         if (tma_copy && !VEC) {         // A = 1..3: TMA load of the whole old ring, shifted write-out by the 32 lanes
             if (t == nphys) {
-                mbar_init(&tma_bar, 1);
                 mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
                 tma_load_2d(smem_raw, &tm_prev, 12, (int)row0, &tma_bar);
             }
@@ -334,11 +333,15 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             else write_shifted_from_smem<1>(tile, o, ac, row0, rows, a.W, a.B, t - nphys, a.copy_threads);
         } else if (tma_copy) {
             if (t == nphys) {           // one lane drives the TMA engine: global -> shared -> global, shifted by one slot
-                mbar_init(&tma_bar, 1);
-                mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
                 // box = ring slots [edge, B-1-edge) of the new obs = slots [edge+1, B-edge) of the old one.  edge = 1 when the
                 // rows are 32-byte aligned: the two sectors shared with the kin part / the newest slot are then written
-                // whole by the drone's own thread (no partial-sector L2 fills from DRAM).
+                // whole by the drone's own thread (no partial-sector L2 fills from DRAM); the two old slots it needs
+                // (1 and B-1) arrive through two more, 16-byte-wide TMA boxes on the same mbarrier.
+                mbar_expect_tx(&tma_bar, (uint32_t)(a.tma_bytes_box + (a.tma_edge ? 2 * a.DPB * 16 : 0)));
+                if (a.tma_edge) {
+                    tma_load_2d(smem_raw + a.tma_bytes - 2 * a.tma_edge_bytes, &tm_edge, 16, (int)row0, &tma_bar);
+                    tma_load_2d(smem_raw + a.tma_bytes - a.tma_edge_bytes, &tm_edge, a.W - 4, (int)row0, &tma_bar);
+                }
                 tma_load_2d(smem_raw, &tm_prev, 12 + 4 * (a.tma_edge + 1), (int)row0, &tma_bar);
                 mbar_wait(&tma_bar, 0);
                 if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 5] = gtime();    // 5: history tile landed in smem
@@ -369,13 +372,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             cnt = a.p.counter[e];
             if (a.auto_reset) ep_ret0 = a.p.ep_ret[e];
         }
-        if constexpr (VEC) {
-            if (a.use_tma && a.tma_edge && a.obs_prev) {
-                const float4* pr = reinterpret_cast<const float4*>(a.obs_prev + d * a.W);
-                edge_lo = ldg_stream(pr + 4);
-                edge_hi = ldg_stream(pr + (a.W >> 2) - 1);
-            }
-        }
+
         if (a.action_type == GPD_ACT_CTRL_RPM) {                 // CtrlAviary.py:140
             V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
             rpm[0] = clip(v.x, R(0), P.MAX_RPM); rpm[1] = clip(v.y, R(0), P.MAX_RPM);
@@ -629,7 +626,13 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
                 const int W4 = a.W >> 2;
                 r[W4 - 1] = make_float4(act[0], act[1], act[2], act[3]);           // newest ring slot, BaseRLAviary.py:187
-                if (a.use_tma && a.tma_edge) { r[3] = edge_lo; r[W4 - 2] = edge_hi; }   // complete the two shared sectors
+                if (edge_smem) {        // complete the two sectors shared with the TMA part from the edge boxes
+                    mbar_wait(&tma_bar, 0);
+                    const float4* elo = reinterpret_cast<const float4*>(smem_raw + a.tma_bytes - 2 * a.tma_edge_bytes);
+                    const float4* ehi = reinterpret_cast<const float4*>(smem_raw + a.tma_bytes - a.tma_edge_bytes);
+                    edge_lo = elo[t]; edge_hi = ehi[t];
+                    r[3] = edge_lo; r[W4 - 2] = edge_hi;
+                }
             } else {
                 float* r = reinterpret_cast<float*>(a.obs_out) + d * a.W;
 #pragma unroll

@@ -7,7 +7,7 @@ using Real = GPD_REAL;
 
 template <bool LEAN, bool MULTI, bool VEC>
 static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, const CUtensorMap& tp, const CUtensorMap& to,
-                                 cudaStream_t st)
+                                 const CUtensorMap& te, cudaStream_t st)
 {
     static size_t smem_set = 48 * 1024;
     if (lc.smem > smem_set) {
@@ -25,16 +25,17 @@ static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, c
     attr[0].val.programmaticStreamSerializationAllowed = lc.pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, step_kernel<Real, LEAN, MULTI, VEC>, a, tp, to);
+    return cudaLaunchKernelEx(&cfg, step_kernel<Real, LEAN, MULTI, VEC>, a, tp, to, te);
 }
 
 template <>
 cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
-                              const CUtensorMap* tm_out, cudaStream_t st)
+                              const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st)
 {
     static const CUtensorMap dummy{};
     const CUtensorMap& tp = tm_prev ? *tm_prev : dummy;
     const CUtensorMap& to = tm_out ? *tm_out : dummy;
+    const CUtensorMap& te = tm_edge ? *tm_edge : dummy;
     const bool rpm_like = a.action_type == GPD_ACT_RPM || a.action_type == GPD_ACT_ONE_D_RPM ||
                           a.action_type == GPD_ACT_CTRL_RPM;
     const bool lean = rpm_like && a.phy == 0;
@@ -42,14 +43,14 @@ cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cons
     const bool vec = a.A == 4 && a.env_kind != GPD_ENV_CTRL && (a.W % 4 == 0);
     const int key = (lean ? 4 : 0) | (multi ? 2 : 0) | (vec ? 1 : 0);
     switch (key) {
-    case 0: return launch_step_t<false, false, false>(a, lc, tp, to, st);
-    case 1: return launch_step_t<false, false, true>(a, lc, tp, to, st);
-    case 2: return launch_step_t<false, true, false>(a, lc, tp, to, st);
-    case 3: return launch_step_t<false, true, true>(a, lc, tp, to, st);
-    case 4: return launch_step_t<true, false, false>(a, lc, tp, to, st);
-    case 5: return launch_step_t<true, false, true>(a, lc, tp, to, st);
-    case 6: return launch_step_t<true, true, false>(a, lc, tp, to, st);
-    default: return launch_step_t<true, true, true>(a, lc, tp, to, st);
+    case 0: return launch_step_t<false, false, false>(a, lc, tp, to, te, st);
+    case 1: return launch_step_t<false, false, true>(a, lc, tp, to, te, st);
+    case 2: return launch_step_t<false, true, false>(a, lc, tp, to, te, st);
+    case 3: return launch_step_t<false, true, true>(a, lc, tp, to, te, st);
+    case 4: return launch_step_t<true, false, false>(a, lc, tp, to, te, st);
+    case 5: return launch_step_t<true, false, true>(a, lc, tp, to, te, st);
+    case 6: return launch_step_t<true, true, false>(a, lc, tp, to, te, st);
+    default: return launch_step_t<true, true, true>(a, lc, tp, to, te, st);
     }
 }
 
