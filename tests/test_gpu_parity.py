@@ -544,3 +544,105 @@ def test_cuda_graphed_rollout_matches_eager_stepping():
     with pytest.raises(ValueError):
         GraphedRollout(env_g, policy, 3)
     env_g.close(); env_e.close()
+
+
+@pytest.mark.parametrize("desc,kw_over,E,steps,tol", [
+    ("DYN+GND+DRAG+DW 3 drones (MUFU downwash, predicate ground-effect gate)",
+     dict(env_kind="multihover", num_drones=3, physics_flags=7), 64, 8, 1e-3),
+    ("Ctrl 3 drones DYN+DW", dict(env_kind="ctrl", action_type="ctrl_rpm", num_drones=3, physics_flags=4, ctrl_freq=48), 64, 12, 1e-3),
+    ("ActionType.PID 48 Hz (TMA ring load + shared-memory shift)", dict(action_type="pid", ctrl_freq=48, model=DroneModel.CF2P), 200, 12, 2e-3),
+    ("ActionType.ONE_D_PID 48 Hz", dict(action_type="one_d_pid", ctrl_freq=48, model=DroneModel.CF2P), 200, 12, 2e-3),
+    ("ActionType.VEL 48 Hz", dict(action_type="vel", ctrl_freq=48, model=DroneModel.CF2P), 200, 12, 2e-3),
+    ("VelocityAviary", dict(env_kind="ctrl", action_type="ctrl_vel", num_drones=2, ctrl_freq=48, model=DroneModel.CF2P), 100, 12, 2e-3),
+    ("ONE_D_RPM 48 Hz (A=1, 16-byte rows)", dict(action_type="one_d_rpm", ctrl_freq=48), 200, 60, 1e-4),
+])
+def test_cuda_f32_other_paths_vs_oracle(desc, kw_over, E, steps, tol):
+    """FP32 throughput mode on every non-headline path (force models with fast math, controllers, A<4 rows) against the
+    FP64 oracle.  Closed-loop controllers amplify rounding (SURVEY finding 6): short horizons, looser tolerance."""
+    rng = np.random.default_rng(abs(hash(desc)) % 2**31)
+    kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    kw.update(kw_over)
+    N, act = kw["num_drones"], kw["action_type"]
+    A = {"rpm": 4, "one_d_rpm": 1, "pid": 3, "one_d_pid": 1, "vel": 4, "ctrl_rpm": 4, "ctrl_vel": 4}[act]
+    if N > 1:
+        # heights 0.2 / 0.4 / 0.55 m: pair gaps 0.15-0.35 m stay away from both singularities of the reference's downwash
+        # (alpha ~ 1/delta_z^2 at delta_z -> 0+, BaseAviary.py:802; beta = 0.16*delta_z - 0.11 -> 0 at 0.6875 m, :803-804),
+        # where any rounding difference is amplified without bound and an FP32 comparison is meaningless
+        z = np.array([0.2, 0.4, 0.55, 0.75, 0.9, 1.05])[None, :N] + rng.uniform(0, 0.01, (E, N))
+        perm = np.argsort(rng.uniform(size=(E, N)), axis=1)
+        z = np.take_along_axis(z, perm, axis=1)
+        xyz = np.stack([rng.uniform(-.15, .15, (E, N)), rng.uniform(-.15, .15, (E, N)), z], -1)
+        kw["init_xyz"], kw["init_rpy"] = xyz, rng.uniform(-.1, .1, (E, N, 3))
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E, precision="f32")
+    sim.reset()
+    hover = load_drone_params(kw["model"]).HOVER_RPM
+    worst = 0.0
+    for t in range(steps):
+        if act == "ctrl_rpm":
+            a = hover * (1 + 0.02 * rng.uniform(-1, 1, (E, N, A)))
+            dev_a = torch.from_numpy(a.astype(np.float32)).cuda()
+            a = a.astype(np.float32).astype(np.float64)            # the oracle sees exactly the FP32 command
+        elif act == "ctrl_vel":
+            a = np.concatenate([rng.uniform(-1, 1, (E, N, 3)), rng.uniform(0, 1, (E, N, 1))], -1).astype(np.float32)
+            dev_a = torch.from_numpy(a).cuda()
+            a = a.astype(np.float64)
+        else:
+            a = (0.3 * rng.uniform(-1, 1, (E, N, A))).astype(np.float32)
+            dev_a = torch.from_numpy(a).cuda()
+        obs, rew, term, trunc = sim.step(dev_a)
+        o_ref, r_ref, _, _ = ref.step(a)
+        st, _, _ = state_np(sim)
+        worst = max(worst, rel_err(st[..., S_POS], ref.state20[..., S_POS]), rel_err(st[..., S_VEL], ref.state20[..., S_VEL], floor=1e-2))
+        if kw["env_kind"] != "ctrl":          # action ring part of the observation is bit-exact in every mode
+            assert np.array_equal(obs.cpu().numpy()[..., 12:], o_ref[..., 12:]), (desc, t)
+    assert worst <= tol, (desc, worst)
+    sim.close()
+
+
+def test_cuda_f32_force_models_vs_f64_kernels():
+    """FP32 fast-math force kernels (MUFU reciprocals / ex2) against the FP64 kernels (which are pinned to the reference's
+    recorded forces) on pairs kept away from the downwash singularities."""
+    import ctypes as C
+    from gpd_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(123)
+    d = _lib.drone_params_c(load_drone_params(DroneModel.CF2X))
+    E, N = 4000, 2
+    pos = np.zeros((E, N, 3))
+    pos[:, 1, 0:2] = rng.uniform(-.3, .3, (E, 2))
+    dz = np.where(rng.uniform(size=E) < 0.5, rng.uniform(0.05, 0.55, E), rng.uniform(0.85, 2.5, E))   # |beta| >= 0.022
+    pos[:, 1, 2] = dz
+    pos[:, 0, :] += rng.uniform(-1, 1, (E, 3))
+    pos[:, 1, :] += pos[:, 0, :]
+    out = {}
+    for prec, dt in ((1, torch.float64), (0, torch.float32)):
+        p_t = torch.as_tensor(pos, dtype=dt).cuda().contiguous()
+        o = torch.empty((E, N), dtype=dt, device="cuda")
+        _lib.check(L.gpd_force_downwash(0, prec, C.byref(d), E, N, C.c_void_p(p_t.data_ptr()), C.c_void_p(o.data_ptr()), None))
+        out[prec] = o.double().cpu().numpy()
+    ref, got = out[1][:, 0], out[0][:, 0]                 # drone 0 sits below drone 1
+    assert np.all(out[1][:, 1] == 0) and np.all(out[0][:, 1] == 0)
+    big = np.abs(ref) > 1e-6
+    assert big.sum() > 500
+    # inputs are rounded to FP32 first: d(force)/d(delta_z) ~ force * (2/dz + dxy^2*0.16/beta^3) amplifies that rounding
+    assert np.max(np.abs(got[big] - ref[big]) / np.abs(ref[big])) <= 5e-4
+    assert np.max(np.abs(got[~big] - ref[~big])) <= 1e-8
+    # ground effect and drag
+    n = 3000
+    rpm = rng.uniform(9000, 20000, (n, 4)); p3 = rng.uniform([-1, -1, 0.01], [1, 1, 1.0], (n, 3)); vel = rng.uniform(-2, 2, (n, 3))
+    q = rng.standard_normal((n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    res = {}
+    for prec, dt in ((1, torch.float64), (0, torch.float32)):
+        t = lambda a: torch.as_tensor(a, dtype=dt).cuda().contiguous()
+        r_, p_, q_, v_ = t(rpm), t(p3), t(q), t(vel)
+        ge = torch.empty((n, 4), dtype=dt, device="cuda"); ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dr = torch.empty((n, 3), dtype=dt, device="cuda")
+        pp = lambda x: C.c_void_p(x.data_ptr())
+        _lib.check(L.gpd_force_ground_effect(0, prec, C.byref(d), n, pp(r_), pp(p_), pp(q_), pp(ge), pp(ok), None))
+        _lib.check(L.gpd_force_drag(0, prec, C.byref(d), n, pp(r_), pp(q_), pp(v_), pp(dr), None))
+        res[prec] = (ge.double().cpu().numpy(), ok.cpu().numpy(), dr.double().cpu().numpy())
+    assert rel_err(res[0][0], res[1][0], floor=1e-9) <= 1e-4
+    assert rel_err(res[0][2], res[1][2], floor=1e-9) <= 1e-4
+    assert np.mean(res[0][1] == res[1][1]) > 0.995          # gate differs only within rounding of the +-pi/2 boundary
