@@ -146,7 +146,7 @@ static size_t smem_bytes(bool f64, bool ctrl, bool multi, int DPB, int EPB)
     size_t rs = f64 ? 8 : 4;
     size_t stage = ctrl ? (size_t)DPB * 20 * rs : 0;
     size_t b = (stage + 15) & ~size_t(15);
-    if (multi) b += (size_t)DPB * 3 * rs + (size_t)DPB * 2 * rs + (size_t)DPB * 4 + (size_t)EPB * 2 * 4;
+    if (multi) b += (size_t)DPB * 4 * rs + (size_t)DPB * 2 * rs + (size_t)DPB * 4 + (size_t)EPB * 2 * 4;
     b += 32;
     return (b + 15) & ~size_t(15);
 }

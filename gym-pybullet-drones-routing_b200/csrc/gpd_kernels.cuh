@@ -75,7 +75,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
 // ---- shared-memory layout -------------------------------------------------------------
 //   tile  : RL envs with A == 4: TMA box of the action history, DPB x (B-1) float4 (a.tma_bytes)
 //   stage : Ctrl env R[DPB*20] (state20 rows)
-//   MULTI : snap R[DPB*3], red R[DPB*2], redi int[DPB], envf int[EPB*2]
+//   MULTI : snap R[DPB*4] (x,y,z,-), red R[DPB*2], redi int[DPB], envf int[EPB*2]
 //   stats : float[4] + int[4]
 template <typename R>
 struct Smem {
@@ -86,7 +86,7 @@ struct Smem {
     __device__ R* stage_r() const { return reinterpret_cast<R*>(base); }
     __device__ size_t stage_bytes() const { return ctrl ? size_t(DPB) * 20 * sizeof(R) : 0; }
     __device__ R* snap() const { return reinterpret_cast<R*>(base + ((stage_bytes() + 15) & ~size_t(15))); }
-    __device__ R* red() const { return snap() + (multi ? size_t(DPB) * 3 : 0); }
+    __device__ R* red() const { return snap() + (multi ? size_t(DPB) * 4 : 0); }
     __device__ int* redi() const { return reinterpret_cast<int*>(red() + (multi ? size_t(DPB) * 2 : 0)); }
     __device__ int* envf() const { return redi() + (multi ? DPB : 0); }
     __device__ float* stat_f() const { return reinterpret_cast<float*>(envf() + (multi ? 2 * EPB : 0)); }
@@ -472,15 +472,19 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             }
             if constexpr (MULTI) {
                 if (a.phy & GPD_PHY_DW) {                        // :362,367 against the substep-start snapshot
-                    R* snap = sm.snap();
+                    V4<R>* snap = reinterpret_cast<V4<R>*>(sm.snap());    // (x, y, z, -) per drone: one 16/32-byte read per pair
                     phys_sync(nphys);
-                    if (t < a.DPB) { snap[3 * t] = s.px; snap[3 * t + 1] = s.py; snap[3 * t + 2] = s.pz; }
+                    if (t < a.DPB) snap[t] = M<R>::make4(s.px, s.py, s.pz, R(0));
                     phys_sync(nphys);
                     R dw = R(0);
-                    const R* env = snap + 3 * (le * a.N);
-                    if (active)
-                        for (int j = 0; j < a.N; ++j)
-                            dw += downwash_pair(P, s.px, s.py, s.pz, env[3 * j], env[3 * j + 1], env[3 * j + 2]);
+                    const V4<R>* env = snap + le * a.N;
+                    if (active) {
+#pragma unroll 4
+                        for (int j = 0; j < a.N; ++j) {
+                            const V4<R> o = env[j];
+                            dw += downwash_pair(P, s.px, s.py, s.pz, o.x, o.y, o.z);
+                        }
+                    }
                     fb[2] += dw;
                     pb = fb;
                 }

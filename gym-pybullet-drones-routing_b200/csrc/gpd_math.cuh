@@ -29,6 +29,9 @@ __device__ __forceinline__ float fast_atan2f(float y, float x)
     return copysignf(r, y);
 }
 
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 template <typename R> struct M;
 template <> struct M<float> {
     static constexpr bool is_double = false;
@@ -250,15 +253,19 @@ __device__ __forceinline__ R downwash_pair(const DevDrone<R>& P, R mx, R my, R m
         }
         return R(0);
     } else {
-        // FP32 throughput mode: the same expression on squared distances with MUFU reciprocals and ex2
-        // (u^2 = dxy^2 / beta^2, so the sqrt of :800 disappears; delta_xy < 10 <=> dxy^2 < 100).
+        // FP32 throughput mode: the same expression on squared distances (u^2 = dxy^2 / beta^2, so the sqrt of :800
+        // disappears; delta_xy < 10 <=> dxy^2 < 100) with ONE raw MUFU reciprocal, r = 1/(delta_z*beta), shared by
+        // 1/delta_z = r*beta and 1/beta = r*delta_z, and one raw MUFU ex2.  Branch-free: every guard (including beta = 0,
+        // where u = inf and the reference's exp(-inf) gives 0) is folded into the final select.
         const float d2 = dx * dx + dy * dy;
-        const float rz = __fdividef(P.PROP_RADIUS * 0.25f, delta_z);
         const float beta = fmaf(P.DW2, delta_z, P.DW3);
-        const float ib = __fdividef(1.0f, beta);
-        const float e = exp2f(-0.72134752044448170368f * d2 * (ib * ib));                  // exp(-0.5 u^2)
+        const float zb = delta_z * beta;
+        const float r = rcp_approx(zb);
+        const float rz = (P.PROP_RADIUS * 0.25f) * (r * beta);
+        const float ib = r * delta_z;
+        const float e = ex2_approx(-0.72134752044448170368f * d2 * (ib * ib));            // exp(-0.5 u^2)
         const float f = -P.DW1 * (rz * rz) * e;
-        return (delta_z > 0.f && d2 < 100.f) ? f : 0.f;
+        return (delta_z > 0.f && d2 < 100.f && fabsf(zb) > 1e-30f) ? f : 0.f;
     }
 }
 
