@@ -646,3 +646,54 @@ def test_cuda_f32_force_models_vs_f64_kernels():
     assert rel_err(res[0][0], res[1][0], floor=1e-9) <= 1e-4
     assert rel_err(res[0][2], res[1][2], floor=1e-9) <= 1e-4
     assert np.mean(res[0][1] == res[1][1]) > 0.995          # gate differs only within rounding of the +-pi/2 boundary
+
+
+def test_cuda_full_size_properties_65536_envs():
+    """BASELINE config size (65,536 HoverAviary envs, FP32): size-independent properties.
+    (1) determinism; (2) env-permutation equivariance (envs are independent: row e depends only on env e's inputs);
+    (3) a 256-env sample agrees with the FP64 oracle within the FP32 tolerance; (4) the observation ring shifts by exactly
+    one slot per step and its newest slot is the action; (5) statistics count every env-step."""
+    E, T = 65536, 24
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    acts = [(torch.rand((E, 1, 4), generator=g, device="cuda") * 2 - 1) * 0.3 for _ in range(T)]
+    perm = torch.randperm(E, generator=g, device="cuda")
+    rng = np.random.default_rng(5)
+    xyz, rpy = _random_init(rng, E, 1)
+    kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=xyz, init_rpy=rpy)
+    p = perm.cpu().numpy()
+    kw_p = dict(kw, init_xyz=xyz[p], init_rpy=rpy[p])
+    a_sim, b_sim, p_sim = (make_sim(kw, E, "f32", auto_reset=True), make_sim(kw, E, "f32", auto_reset=True),
+                           make_sim(kw_p, E, "f32", auto_reset=True))
+    sample = np.sort(rng.choice(E, 256, replace=False))
+    ref = make_oracle(dict(kw, init_xyz=xyz[sample], init_rpy=rpy[sample]), num_envs=256)
+    for s in (a_sim, b_sim, p_sim):
+        s.reset()
+    prev = a_sim.obs.clone()
+    worst = 0.0
+    alive = np.ones(256, bool)
+    for t in range(T):
+        oa, ra, ta, tra = a_sim.step(acts[t])
+        ob, rb, tb, trb = b_sim.step(acts[t])
+        op, rp, tp, trp = p_sim.step(acts[t][perm].contiguous())
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(tra, trb)      # (1)
+        assert torch.equal(oa[perm], op) and torch.equal(ra[perm], rp) and torch.equal(tra[perm], trp)            # (2)
+        assert torch.equal(oa[..., 12:68], prev[..., 16:72]) and torch.equal(oa[..., 68:72], acts[t])            # (4)
+        prev = oa.clone()
+        o_ref, r_ref, te_ref, tr_ref = ref.step(acts[t][sample].cpu().numpy())
+        done = (te_ref | tr_ref).astype(bool)
+        flags = (ta | tra).cpu().numpy().astype(bool)[sample]
+        alive &= ~(flags != done)            # an FP32 flag flip right at a threshold ends the comparison for that env
+        st = a_sim.get_state()[0].double().cpu().numpy()[sample]
+        chk = alive & ~done
+        if chk.any():
+            worst = max(worst, rel_err(st[chk][:, 0, S_POS], ref.state20[chk][:, 0, S_POS]))
+        if done.any():
+            ref.reset(done.astype(np.uint8))
+        alive &= ~done                       # after a reset the FP32/FP64 episodes restart in lockstep only if flags agreed
+        alive |= done & (flags == done)
+    assert alive.mean() > 0.9 and worst <= 1e-4, (alive.mean(), worst)                                            # (3)
+    stats = a_sim.episode_stats()
+    assert stats[6] == E * T and stats[0] > 0                                                                     # (5)
+    for s in (a_sim, b_sim, p_sim):
+        s.close()
