@@ -16,7 +16,7 @@ from gpd_b200.envs import HoverAviary  # noqa: E402
 from gpd_b200.utils.enums import Physics  # noqa: E402
 
 
-def run(E=65536, nsets=8, tpb=128, env=None, auto_reset=True, reps=60, trials=3, ctrl_freq=30, precision="f32", graph=True, pyb_freq=240):
+def run(E=65536, nsets=8, tpb=0, env=None, auto_reset=True, reps=60, trials=3, ctrl_freq=30, precision="f32", graph=True, pyb_freq=240, streams=1):
     old = {}
     for k, v in (env or {}).items():
         old[k] = os.environ.get(k)
@@ -35,9 +35,27 @@ def run(E=65536, nsets=8, tpb=128, env=None, auto_reset=True, reps=60, trials=3,
         e.reset()
     period = 2 * nsets
 
+    extra = [torch.cuda.Stream() for _ in range(streams - 1)]
+
     def cycle():
+        if streams == 1:
+            for k in range(period):
+                envs[k % nsets]._sim.step(acts[k])
+            return
+        # independent env sets round-robin over `streams` streams (fork/join with events; capturable)
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in extra:
+            st.wait_event(fork)
         for k in range(period):
-            envs[k % nsets]._sim.step(acts[k])
+            st = main if k % streams == 0 else extra[k % streams - 1]
+            with torch.cuda.stream(st):
+                envs[k % nsets]._sim.step(acts[k])
+        for st in extra:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
     for _ in range(3):
         cycle()
     torch.cuda.synchronize()
