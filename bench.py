@@ -59,7 +59,10 @@ def workload_name(a):
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (oracle/gpd_oracle.c) on the host cores.  The reference itself is pure Python and
 # cannot travel to the GPU box (no /root/reference there), so kind = "port".
-def cpu_run(a, seconds=None, steps=None, warmup=2):
+def cpu_run(a, seconds=None, steps=None, warmup=2, budget_s=120.0):
+    """The oracle port on all host cores.  With a fixed number of `steps` the per-step sample (number of envs, at most
+    the bench's own) is sized from a calibration step so that the whole run stays within `budget_s`: the metric is
+    per drone-substep, and the CPU cost is linear in the number of envs."""
     from gpd_b200.params import load_drone_params
     from gpd_b200.utils.enums import DroneModel
     from oracle import oracle as orc
@@ -75,8 +78,21 @@ def cpu_run(a, seconds=None, steps=None, warmup=2):
         done = (te | tr)
         if done.any():
             sim.reset(done)
+        return sim
     for k in range(warmup):
         one(k)
+    if steps is not None:
+        # size the per-step sample from two calibration steps of the real loop; never below 8192 envs, where the
+        # per-step thread fork/join would start to dominate and under-state the CPU
+        t0 = time.perf_counter()
+        one(0); one(1)
+        per_step = (time.perf_counter() - t0) / 2
+        if per_step * steps > budget_s and E > 8192:
+            E = max(8192, int(E * budget_s / (per_step * steps)))
+            sim = orc.OracleSim(load_drone_params(DroneModel.CF2X), E, ctrl_freq=a.ctrl_freq)
+            pool = [p[:E].copy() for p in pool]
+            for k in range(warmup):
+                one(k)
     t0 = time.perf_counter()
     n = 0
     while True:
@@ -213,22 +229,33 @@ def b200_arm(a):
     for _ in range((wu + period - 1) // period):
         cycle()
     torch.cuda.synchronize()
-    graph = None
+    K = max(1, a.steps)
+    reps, tail = divmod(K, period)          # EXACTLY K steps: `reps` replays of the 16-step graph + one tail graph
+
+    def run_tail():
+        for k in range(tail):
+            envs[k % nsets]._sim.step(acts[k])
+    graph = tail_graph = None
     if not a.no_graph:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 cycle()
+            if tail:
+                saved = [(e._sim._cur, e._sim._have_prev) for e in envs]
+                tail_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(tail_graph, stream=side):
+                    run_tail()
+                for e, (c, h) in zip(envs, saved):      # capture only records: restore the host-side ping-pong phase
+                    e._sim._cur, e._sim._have_prev = c, h
         torch.cuda.synchronize()
         graph.replay()
         torch.cuda.synchronize()
-    reps = max(1, (a.steps + period - 1) // period)
-    K = reps * period
 
     sampler = ClockSampler(local)
     if graph is not None:           # bring the clocks to their loaded state before sampling starts
-        for _ in range(max(1, reps // 4)):
+        for _ in range(max(1, min(reps // 4, 500))):
             graph.replay()
     if world > 1:
         dist.barrier()
@@ -241,6 +268,11 @@ def b200_arm(a):
             graph.replay()
         else:
             cycle()
+    if tail:
+        if tail_graph is not None:
+            tail_graph.replay()
+        else:
+            run_tail()
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -315,7 +347,8 @@ def b200_arm(a):
             "dtype": a.precision, "data": "synthetic",
             "config": {"workload": workload_name(a), "envs_per_gpu": E, "substeps_per_step": S,
                        "l2": f"rotating {nsets} env sets per GPU (~{nsets * E * 700 / 1e6:.0f} MB touched per cycle > 126 MB L2)",
-                       "launch": "CUDA graph of %d step kernels" % period if graph is not None else "direct launches",
+                       "launch": ("CUDA graph of %d step kernels x %d replays + %d-step tail graph" % (period, reps, tail))
+                       if graph is not None else "direct launches",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "drone-substeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
