@@ -2,7 +2,9 @@
 (``:35-39``), ``computeControlFromState`` (``:55-93``), ``setPIDCoefficients`` (``:138-177``)."""
 import numpy as np
 
-from ..params import load_drone_params
+import xml.etree.ElementTree as etxml
+
+from ..params import load_drone_params, urdf_path
 from ..utils.enums import DroneModel
 
 
@@ -38,3 +40,20 @@ class BaseControl(object):
         for name, val in zip(ATTR_LIST, [p_coeff_pos, i_coeff_pos, d_coeff_pos, p_coeff_att, i_coeff_att, d_coeff_att]):
             if val is not None:
                 setattr(self, name, np.asarray(val, dtype=np.float64))
+
+    def _getURDFParameter(self, parameter_name: str):
+        """Reads one parameter of the controller's drone model from its URDF (reference BaseControl.py:181-216)."""
+        root = etxml.parse(urdf_path(self.DRONE_MODEL)).getroot()
+        base = root.find("link")
+        if parameter_name == 'm':
+            return float(base.find("inertial").find("mass").attrib['value'])
+        if parameter_name in ['ixx', 'iyy', 'izz']:
+            return float(base.find("inertial").find("inertia").attrib[parameter_name])
+        if parameter_name in ['arm', 'thrust2weight', 'kf', 'km', 'max_speed_kmh', 'gnd_eff_coeff', 'prop_radius',
+                              'drag_coeff_xy', 'drag_coeff_z', 'dw_coeff_1', 'dw_coeff_2', 'dw_coeff_3']:
+            return float(root.find("properties").attrib[parameter_name])
+        if parameter_name in ['length', 'radius']:
+            return float(base.find("collision").find("geometry").find("cylinder").attrib[parameter_name])
+        if parameter_name == 'collision_z_offset':
+            return [float(v) for v in base.find("collision").find("origin").attrib['xyz'].split()][2]
+        return None

@@ -77,3 +77,15 @@ class DSLPIDControl(BaseControl):
                                              p(tv), p(trr), p(self.state), p(rpm), p(pos_e), p(yaw_e), st))
         self._keepalive = (cp, cq, cv, tp, tr, tv, trr)
         return rpm, pos_e, yaw_e
+
+    def _one23DInterface(self, thrust):
+        """1, 2 or 4 thrust inputs -> 4 motor PWMs (reference DSLPIDControl.py:263-287); ``thrust``: (..., DIM)."""
+        t = torch.as_tensor(thrust, dtype=self.real, device=self.device)
+        DIM = t.shape[-1]
+        pwm = torch.clamp((torch.sqrt(t / (self.KF * (4 / DIM))) - self.PWM2RPM_CONST) / self.PWM2RPM_SCALE,
+                          self.MIN_PWM, self.MAX_PWM)
+        if DIM in (1, 4):
+            return torch.repeat_interleave(pwm, 4 // DIM, dim=-1)
+        if DIM == 2:
+            return torch.cat([pwm, torch.flip(pwm, dims=(-1,))], dim=-1)
+        raise ValueError("[ERROR] in DSLPIDControl._one23DInterface()")

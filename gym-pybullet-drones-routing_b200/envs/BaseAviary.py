@@ -198,6 +198,30 @@ class BaseAviary:
         d = torch.linalg.norm(p[:, :, None, :] - p[:, None, :, :], dim=-1)
         return (d < self.NEIGHBOURHOOD_RADIUS).to(p.dtype)
 
+    def _calculateNextStep(self, current_position, destination, step_size=1):
+        """Intermediate waypoint at most ``step_size`` from the current position (BaseAviary.py:1105-1147);
+        batched over the leading axes: (..., 3) tensors."""
+        cur = torch.as_tensor(current_position)
+        dest = torch.as_tensor(destination, dtype=cur.dtype, device=cur.device)
+        direction = dest - cur
+        distance = torch.linalg.norm(direction, dim=-1, keepdim=True)
+        nxt = cur + direction / distance.clamp_min(torch.finfo(cur.dtype).tiny) * step_size
+        return torch.where(distance <= step_size, dest.expand_as(cur), nxt)
+
+    def checkpoint(self):
+        """Everything needed to resume bit-exactly: integrator state, controller state, counters and the current
+        observation (which carries the action ring)."""
+        st, rr, ps, cnt = self._sim.get_state()
+        return {"state20": st.clone(), "rpy_rates": rr.clone(), "pid_state": ps.clone(), "step_counter": cnt.clone(),
+                "obs": self._sim.obs.clone()}
+
+    def restore(self, ckpt):
+        sim = self._sim
+        sim.set_state(ckpt["state20"], ckpt["rpy_rates"], ckpt["pid_state"], ckpt["step_counter"])
+        sim.obs_buf[sim._cur].copy_(ckpt["obs"])
+        sim._have_prev = True
+        self._state_cache = None
+
     #### hooks of the subclasses (BaseAviary.py:1018-1101) ############################
     def _actionSpace(self):
         raise NotImplementedError

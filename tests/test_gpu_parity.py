@@ -697,3 +697,33 @@ def test_cuda_full_size_properties_65536_envs():
     assert stats[6] == E * T and stats[0] > 0                                                                     # (5)
     for s in (a_sim, b_sim, p_sim):
         s.close()
+
+
+def test_cuda_checkpoint_restore_and_helpers():
+    """env.checkpoint()/restore() resume a HoverAviary run bit-exactly, ring included; batched helper methods."""
+    from gpd_b200.control.DSLPIDControl import DSLPIDControl
+    from gpd_b200.envs import HoverAviary
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    E = 500
+    acts = [(torch.rand((E, 1, 4), generator=g, device="cuda") * 2 - 1) * 0.2 for _ in range(12)]
+    a = HoverAviary(num_envs=E, precision="f32")
+    a.reset()
+    for t in range(6):
+        a.step(acts[t])
+    ck = a.checkpoint()
+    b = HoverAviary(num_envs=E, precision="f32")
+    b.reset()
+    b.restore(ck)
+    for t in range(6, 12):
+        oa, ra, _, _, _ = a.step(acts[t])
+        ob, rb, _, _, _ = b.step(acts[t])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb)
+    cur = torch.tensor([[0., 0., 0.], [0., 0., 0.]], device="cuda")
+    dst = torch.tensor([[0.3, 0., 0.4], [3., 0., 4.]], device="cuda")
+    nxt = a._calculateNextStep(cur, dst, 1)
+    assert torch.allclose(nxt, torch.tensor([[0.3, 0., 0.4], [0.6, 0., 0.8]], device="cuda"))
+    c = DSLPIDControl(DroneModel.CF2X, num=1)
+    pwm = c._one23DInterface(torch.tensor([[0.3]], dtype=torch.float64))
+    want = min(max((np.sqrt(0.3 / (c.KF * 4)) - 4070.3) / 0.2685, 20000), 65535)
+    assert pwm.shape == (1, 4) and abs(float(pwm[0, 0]) - want) < 1e-6
+    a.close(); b.close()

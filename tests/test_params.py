@@ -38,3 +38,13 @@ def test_enum_values():
     assert Physics("dyn") is Physics.DYN and Physics("pyb_gnd_drag_dw") is Physics.PYB_GND_DRAG_DW
     assert [a.value for a in ActionType] == ["rpm", "pid", "vel", "one_d_rpm", "one_d_pid"]
     assert [o.value for o in ObservationType] == ["kin", "rgb"]
+
+
+def test_base_control_urdf_parameter_lookup():
+    from gpd_b200.control.BaseControl import BaseControl
+    c = BaseControl(DroneModel.CF2X)
+    ref = constants()["models"]["cf2x"]
+    assert c._getURDFParameter('m') == ref["M"] and c._getURDFParameter('kf') == ref["KF"]
+    assert c._getURDFParameter('ixx') == ref["J"][0][0] and c._getURDFParameter('arm') == ref["L"]
+    assert c._getURDFParameter('length') == ref["COLLISION_H"] and c._getURDFParameter('collision_z_offset') == 0.0
+    assert c.GRAVITY == ref["GRAVITY"] and c.KM == ref["KM"]
