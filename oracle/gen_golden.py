@@ -18,6 +18,7 @@ What is recorded (all float64 unless noted; NumPy version stored in every file):
                         values; NOT a reference mode — SURVEY §8a)
   reset_quirks.npz      ring/controller survival across reset(), truncation clock
   logger.npz            utils/Logger.py arrays and CSV texts for a small random log
+  pidpy_dyn.npz         BASELINE configs[0]: the examples/pid.py loop on Physics.DYN, first 40 ctrl steps
 """
 import argparse
 import contextlib
@@ -200,6 +201,48 @@ def gen_velocity(R, out):
     np.savez_compressed(os.path.join(out, "traj_velocity2_cf2p_48.npz"), actions=acts, kind="ctrl_vel", env="VelocityAviary",
                         model="cf2p", ctrl_freq=48, pyb_freq=240, num_drones=n, act_type="ctrl_vel", init_xyz=xyz,
                         init_rpy=rpy, numpy=np.__version__, **rec)
+
+
+def gen_pidpy(R, out):
+    """BASELINE configs[0]: examples/pid.py wired exactly as the script (examples/pid.py:65-77,101-151) on Physics.DYN:
+    CtrlAviary + one DSLPIDControl per drone tracking the circle trajectory, 240 Hz sim / 48 Hz ctrl.  The closed loop is
+    chaotic (SURVEY finding 6; CF2X flips within ~14 ctrl steps, finding 5), so only the first 40 ctrl steps are kept."""
+    P, DM = R["Physics"], R["DroneModel"]
+    res = {}
+    for model, n in ((DM.CF2X, 1), (DM.CF2P, 3)):
+        ctrl_hz, H, H_STEP, RAD = 48, .1, .05, .3
+        INIT_XYZS = np.array([[RAD * np.cos((i / 6) * 2 * np.pi + np.pi / 2), RAD * np.sin((i / 6) * 2 * np.pi + np.pi / 2) - RAD,
+                               H + i * H_STEP] for i in range(n)])
+        INIT_RPYS = np.array([[0, 0, i * (np.pi / 2) / n] for i in range(n)])
+        NUM_WP = ctrl_hz * 10
+        TARGET_POS = np.zeros((NUM_WP, 3))
+        for i in range(NUM_WP):
+            TARGET_POS[i, :] = (RAD * np.cos((i / NUM_WP) * (2 * np.pi) + np.pi / 2) + INIT_XYZS[0, 0],
+                                RAD * np.sin((i / NUM_WP) * (2 * np.pi) + np.pi / 2) - RAD + INIT_XYZS[0, 1], 0)
+        wp = np.array([int((i * NUM_WP / 6) % NUM_WP) for i in range(n)])
+        with quiet():
+            env = R["CtrlAviary"](drone_model=model, num_drones=n, initial_xyzs=INIT_XYZS, initial_rpys=INIT_RPYS,
+                                  physics=P.DYN, neighbourhood_radius=10, pyb_freq=240, ctrl_freq=ctrl_hz, gui=False,
+                                  record=False, obstacles=False, user_debug_gui=False)
+            ctrl = [R["DSLPIDControl"](drone_model=model) for _ in range(n)]
+        action = np.zeros((n, 4))
+        T = 40
+        obs_log, act_log = [], []
+        for i in range(T):
+            with quiet():
+                obs, *_ = env.step(action)
+                for j in range(n):
+                    action[j, :], _, _ = ctrl[j].computeControlFromState(
+                        control_timestep=env.CTRL_TIMESTEP, state=obs[j],
+                        target_pos=np.hstack([TARGET_POS[wp[j], 0:2], INIT_XYZS[j, 2]]), target_rpy=INIT_RPYS[j, :])
+            for j in range(n):
+                wp[j] = wp[j] + 1 if wp[j] < (NUM_WP - 1) else 0
+            obs_log.append(np.array(obs)); act_log.append(action.copy())
+        k = model.value
+        res[k + "_init_xyz"], res[k + "_init_rpy"], res[k + "_waypoints"] = INIT_XYZS, INIT_RPYS, TARGET_POS
+        res[k + "_wp0"] = np.array([int((i * NUM_WP / 6) % NUM_WP) for i in range(n)], np.int32)
+        res[k + "_obs"], res[k + "_actions"] = np.array(obs_log), np.array(act_log)
+    np.savez_compressed(os.path.join(out, "pidpy_dyn.npz"), numpy=np.__version__, **res)
 
 
 def gen_logger(R, out):
@@ -466,12 +509,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,velocity,pid,forces,composite,reset,logger")
+    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,velocity,pid,forces,composite,reset,logger,pidpy")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     R = _load_reference(a.ref)
     gens = dict(constants=gen_constants, traj=gen_traj, velocity=gen_velocity, pid=gen_pid, forces=gen_forces,
-                composite=gen_composite, reset=gen_reset_quirks, logger=gen_logger)
+                composite=gen_composite, reset=gen_reset_quirks, logger=gen_logger, pidpy=gen_pidpy)
     for name, fn in gens.items():
         if not a.only or name in a.only.split(","):
             fn(R, a.out)

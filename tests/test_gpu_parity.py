@@ -727,3 +727,36 @@ def test_cuda_checkpoint_restore_and_helpers():
     want = min(max((np.sqrt(0.3 / (c.KF * 4)) - 4070.3) / 0.2685, 20000), 65535)
     assert pwm.shape == (1, 4) and abs(float(pwm[0, 0]) - want) < 1e-6
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("model", ["cf2x", "cf2p"])
+def test_cuda_pidpy_config0_rollout(model):
+    """BASELINE configs[0] (examples/pid.py on Physics.DYN): the in-kernel loop gpd_rollout_pid, one launch per ctrl step
+    so every step can be compared with the reference's recorded observations and actions (FP64)."""
+    from gpd_b200.sim import BatchedSim
+    g = load_golden("pidpy_dyn.npz")
+    xyz, rpy, wps = g[model + "_init_xyz"], g[model + "_init_rpy"], g[model + "_waypoints"]
+    n, E = xyz.shape[0], 5
+    dm = DroneModel(model)
+    sim = BatchedSim(load_drone_params(dm), E, n, env_kind="ctrl", action_type="ctrl_rpm", pyb_freq=240, ctrl_freq=48,
+                     precision="f64", pid=default_pid_params(dm), init_xyz=xyz, init_rpy=rpy)
+    wp = torch.as_tensor(np.tile(g[model + "_wp0"][None], (E, 1)), dtype=torch.int32).cuda().contiguous()
+    act = torch.zeros((E, n, 4), dtype=torch.float64, device="cuda")
+    wps_t = torch.as_tensor(wps).cuda()
+    ref_obs, ref_act = g[model + "_obs"], g[model + "_actions"]
+    for t in range(ref_obs.shape[0]):
+        sim.rollout_pid(1, wps_t, wp, act)
+        st = sim.get_state()[0].cpu().numpy()
+        tol = 1e-9 if t < 20 else 1e-6
+        for e in (0, E - 1):
+            assert rel_err(st[e][:, 0:3], ref_obs[t][:, 0:3]) <= tol, t
+            assert quat_err(st[e][:, 3:7], ref_obs[t][:, 3:7]) <= tol, t
+            assert rel_err(act.cpu().numpy()[e], ref_act[t]) <= tol * 10, t
+    # and the whole thing in ONE launch reproduces the stepwise result
+    sim2 = BatchedSim(load_drone_params(dm), E, n, env_kind="ctrl", action_type="ctrl_rpm", pyb_freq=240, ctrl_freq=48,
+                      precision="f64", pid=default_pid_params(dm), init_xyz=xyz, init_rpy=rpy)
+    wp2 = torch.as_tensor(np.tile(g[model + "_wp0"][None], (E, 1)), dtype=torch.int32).cuda().contiguous()
+    act2 = torch.zeros((E, n, 4), dtype=torch.float64, device="cuda")
+    sim2.rollout_pid(ref_obs.shape[0], wps_t, wp2, act2)
+    assert torch.equal(sim2.get_state()[0], sim.get_state()[0]) and torch.equal(act2, act) and torch.equal(wp2, wp)
+    sim.close(); sim2.close()

@@ -158,3 +158,28 @@ def test_oracle_threads_agree():
         s1.step(a[t], nthreads=1)
         s4.step(a[t], nthreads=4)
     assert np.array_equal(s1.state20, s4.state20) and np.array_equal(s1.obs, s4.obs)
+
+
+@pytest.mark.parametrize("model", ["cf2x", "cf2p"])
+def test_oracle_pidpy_config0(model):
+    """BASELINE configs[0]: the examples/pid.py loop on Physics.DYN (closed loop, first 40 ctrl steps)."""
+    g = load_golden("pidpy_dyn.npz")
+    xyz, rpy, wps = g[model + "_init_xyz"], g[model + "_init_rpy"], g[model + "_waypoints"]
+    n = xyz.shape[0]
+    dm = DroneModel(model)
+    kw = dict(model=dm, env_kind="ctrl", action_type="ctrl_rpm", num_drones=n, pyb_freq=240, ctrl_freq=48,
+              physics_flags=0, init_xyz=xyz, init_rpy=rpy)
+    sim = make_oracle(kw)
+    pid = orc.make_pid(default_pid_params(dm))
+    pst = np.zeros((n, 9)); action = np.zeros((1, n, 4)); wp = g[model + "_wp0"].copy()
+    ref_obs, ref_act = g[model + "_obs"], g[model + "_actions"]
+    for t in range(ref_obs.shape[0]):
+        obs, _, _, _ = sim.step(action)
+        for j in range(n):
+            s = obs[0, j]
+            action[0, j], _, _ = orc.pid_compute(pid, 1 / 48, s[0:3], s[3:7], s[10:13], [wps[wp[j], 0], wps[wp[j], 1], xyz[j, 2]],
+                                                 rpy[j], None, None, pst[j])
+        wp = np.where(wp < wps.shape[0] - 1, wp + 1, 0)
+        tol = 1e-9 if t < 20 else 1e-6          # chaotic closed loop: 1-ulp differences grow (SURVEY finding 6)
+        assert rel_err(obs[0][:, 0:3], ref_obs[t][:, 0:3]) <= tol, t
+        assert rel_err(action[0], ref_act[t]) <= tol * 10, t
