@@ -261,13 +261,6 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.tma_bytes_box = s->tma_bytes_box;
     a.tma_edge = s->tma_edge;
     a.tma_edge_bytes = s->tma_edge_bytes;
-    {
-        const char* ev = getenv("GPD_STAGGER_NS");
-        const char* eg = getenv("GPD_STAGGER_GROUPS");
-        a.stagger_ns = ev ? atoi(ev) : 0;
-        a.stagger_groups = eg ? atoi(eg) : 2;
-        if (a.stagger_groups < 1) a.stagger_groups = 1;
-    }
     a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207

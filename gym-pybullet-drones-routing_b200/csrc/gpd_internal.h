@@ -82,7 +82,6 @@ struct StepArgs {
     int32_t use_tma;        // history moved by TMA tensor copies (needs obs_prev and float4-granular rows)
     int32_t tma_bytes;      // shared-memory bytes reserved for the TMA tile (multiple of 128)
     int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1-2*tma_edge) * 16
-    int32_t stagger_ns, stagger_groups;   // experimental: delay CTA group g by g*stagger_ns after the PDL wait
     int32_t tma_edge_bytes; // shared-memory bytes of one edge box (DPB*16 rounded up to 128)
     int32_t tma_edge;       // 1: rows are 32-byte aligned, the box skips the first and last shifted slot (written by the drone's thread)
     R dt, ctrl_dt, speed_limit;

@@ -308,10 +308,6 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     if (a.auto_reset && t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
     if (a.auto_reset || edge_smem) __syncthreads();
     pdl_wait();                         // everything above touched only parameters and shared memory
-    if (a.stagger_ns > 0) {             // de-phase the CTAs of a single-wave launch: odd groups start their loads later
-        const unsigned g = blockIdx.x % (unsigned)a.stagger_groups;
-        if (g) __nanosleep(g * (unsigned)a.stagger_ns);
-    }
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
 
     if (!ctrl && !tma_copy)             // no TMA for this row shape (A = 3 or 1) or no previous observation: every thread
