@@ -128,6 +128,4 @@ template <typename R> cudaError_t launch_downwash(const DevDrone<R>& d, int64_t 
 template <typename R> cudaError_t launch_rollout_pid(const StepArgs<R>& a, int n_steps, const R* waypoints, int n_wp,
                                                      int32_t* wp_counters, R* action, cudaStream_t st);
 
-size_t step_smem_bytes(int precision, int env_kind, int N, int DPB, int EPB);
-
 }  // namespace gpd

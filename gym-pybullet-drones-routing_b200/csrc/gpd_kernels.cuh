@@ -4,9 +4,11 @@
 // One thread per drone; a block owns EPB whole envs (DPB = EPB*N consecutive drones), so the
 // per-env reductions (MultiHover reward/termination, downwash) stay inside shared memory.
 // The 13-float integrator state lives in registers across the whole PYB_STEPS_PER_CTRL loop.
-// Observation rows are contiguous per block tile: the kinematic part is staged in shared memory
-// and written with coalesced 16-byte stores; the action-history part is a shifted global->global
-// copy of the previous observation (the RL observation IS the action ring, BaseRLAviary.py:317-318).
+// The RL observation IS the action ring (BaseRLAviary.py:317-318): its history part is a one-slot-shifted copy of the
+// previous observation, moved by TMA tensor copies issued by a dedicated DMA warp (A = 4), by a TMA load plus a
+// shared-memory funnel shift (A = 1..3 with 16-byte rows) or by a register copy (other shapes); each drone's own thread
+// writes the 48-byte kinematic part and the newest ring slot.  The Ctrl observation (state20 rows) is staged in shared
+// memory and written as one contiguous tile.
 #pragma once
 
 #include "gpd_math.cuh"
@@ -35,7 +37,6 @@ __device__ __forceinline__ unsigned long long gtime()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define GPD_STAMP(slot) do { if (a.timeline && stamp_lane) a.timeline[(int64_t)blockIdx.x * 8 + (slot)] = gtime(); } while (0)
 
 // Physics-only barrier (named barrier 1): the DMA/copy warp of the block never joins it.
 __device__ __forceinline__ void phys_sync(int nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
@@ -299,7 +300,6 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool spec = a.copy_threads > 0;
     const bool run_physics = t < nphys;
 
-    const bool stamp_lane = (t == 0) || (t == nphys);
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 0] = gtime();      // 0: CTA start (params fetched)
     pdl_launch_dependents();
     const bool tma_copy = spec && a.use_tma;
