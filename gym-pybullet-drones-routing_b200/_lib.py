@@ -27,7 +27,7 @@ SYMBOLS = [
     "gpd_action_width", "gpd_substeps", "gpd_set_init_poses", "gpd_reset", "gpd_step", "gpd_step_host",
     "gpd_reset_host", "gpd_get_state", "gpd_set_state", "gpd_pid_compute", "gpd_force_ground_effect",
     "gpd_force_drag", "gpd_force_downwash", "gpd_rollout_pid", "gpd_episode_stats", "gpd_grid_size",
-    "gpd_set_timeline_buffer",
+    "gpd_set_timeline_buffer", "gpd_count_nonfinite",
 ]
 
 
@@ -150,6 +150,7 @@ def load(path: str | None = None):
     L.gpd_rollout_pid.argtypes = [vp, i32, vp, i32, vp, vp, vp]
     L.gpd_episode_stats.argtypes = [vp, C.POINTER(dbl), C.c_int, vp]
     L.gpd_grid_size.argtypes = [vp]
+    L.gpd_count_nonfinite.argtypes = [vp, C.POINTER(C.c_longlong), vp]
     L.gpd_set_timeline_buffer.argtypes = [vp, vp]
     if path is None:
         _lib = L

@@ -260,6 +260,10 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.tma_bytes = s->tma_bytes;
     a.tma_bytes_box = s->tma_bytes_box;
     a.tma_edge = s->tma_edge;
+    {
+        const char* ev = getenv("GPD_PDL_EARLY");
+        a.pdl_trigger_early = ev ? atoi(ev) : (s->lc.grid <= 296 ? 1 : 0);
+    }
     a.tma_edge_bytes = s->tma_edge_bytes;
     a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
@@ -641,6 +645,22 @@ int gpd_rollout_pid(gpd_sim* s, int32_t n_ctrl_steps, const void* waypoints, int
         CU(launch_rollout_pid<double>(s->a64, n_ctrl_steps, (const double*)waypoints, n_wp, wp_counters, (double*)action, (cudaStream_t)stream));
     else
         CU(launch_rollout_pid<float>(s->a32, n_ctrl_steps, (const float*)waypoints, n_wp, wp_counters, (float*)action, (cudaStream_t)stream));
+    return GPD_OK;
+}
+
+int gpd_count_nonfinite(gpd_sim* s, long long* out_host, void* stream)
+{
+    if (!s || !out_host) return fail(GPD_ERR_INVALID, "gpd_count_nonfinite: null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* cnt = (unsigned long long*)s->stats_out;       // reuse the 64-byte scratch
+    CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    if (s->cfg.precision == GPD_F64) CU(launch_nonfinite<double>(s->a64, cnt, st));
+    else CU(launch_nonfinite<float>(s->a32, cnt, st));
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_host = (long long)h;
     return GPD_OK;
 }
 

@@ -82,6 +82,7 @@ struct StepArgs {
     int32_t use_tma;        // history moved by TMA tensor copies (needs obs_prev and float4-granular rows)
     int32_t tma_bytes;      // shared-memory bytes reserved for the TMA tile (multiple of 128)
     int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1-2*tma_edge) * 16
+    int32_t pdl_trigger_early; // PDL: release the dependent launch at CTA start (small grids) or after this CTA's stores
     int32_t tma_edge_bytes; // shared-memory bytes of one edge box (DPB*16 rounded up to 128)
     int32_t tma_edge;       // 1: rows are 32-byte aligned, the box skips the first and last shifted slot (written by the drone's thread)
     R dt, ctrl_dt, speed_limit;
@@ -125,6 +126,7 @@ template <typename R> cudaError_t launch_drag(const DevDrone<R>& d, int64_t n, c
                                               const R* vel, R* out, cudaStream_t st);
 template <typename R> cudaError_t launch_downwash(const DevDrone<R>& d, int64_t E, int N, const R* pos, R* out,
                                                   cudaStream_t st);
+template <typename R> cudaError_t launch_nonfinite(const StepArgs<R>& a, unsigned long long* out, cudaStream_t st);
 template <typename R> cudaError_t launch_rollout_pid(const StepArgs<R>& a, int n_steps, const R* waypoints, int n_wp,
                                                      int32_t* wp_counters, R* action, cudaStream_t st);
 

@@ -301,7 +301,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool run_physics = t < nphys;
 
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 0] = gtime();      // 0: CTA start (params fetched)
-    pdl_launch_dependents();
+    if (a.pdl_trigger_early) pdl_launch_dependents();
     const bool tma_copy = spec && a.use_tma;
     const bool edge_smem = tma_copy && VEC && a.tma_edge;       // physics threads read the two edge slots from shared memory
     if (tma_copy && t == nphys) mbar_init(&tma_bar, 1);
@@ -642,6 +642,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }
     }   // run_physics
 
+    if (!a.pdl_trigger_early) pdl_launch_dependents();   // this CTA has issued all its loads and (physics warps) stores
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 4] = gtime();      // 4: physics thread 0 stored everything
     // ---- Ctrl observation tile: coalesced write of the staged state20 rows (contiguous in global memory) ----
     if (ctrl || a.auto_reset) __syncthreads();
@@ -786,6 +787,23 @@ __global__ void set_state_kernel(const StepArgs<R> a, const R* __restrict__ stat
     store_state(a.p, d, s);
     if (pid_state && a.p.pid)
         for (int k = 0; k < 9; ++k) a.p.pid[(int64_t)k * a.D + d] = pid_state[d * 9 + k];
+}
+
+// ---- failure detection: count drones with a non-finite integrator state ----
+template <typename R>
+__global__ void nonfinite_kernel(const StepArgs<R> a, unsigned long long* __restrict__ out)
+{
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (d < a.D) {
+        State<R> s;
+        load_state(a.p, d, s);
+        const R v[13] = { s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, s.wx, s.wy, s.wz };
+#pragma unroll
+        for (int k = 0; k < 13; ++k) bad |= !isfinite(v[k]);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 
 // ---- batched DSLPIDControl.computeControl (control/DSLPIDControl.py:82-145) ----

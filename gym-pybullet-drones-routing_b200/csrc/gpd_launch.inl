@@ -130,4 +130,11 @@ cudaError_t launch_rollout_pid<Real>(const StepArgs<Real>& a, int n_steps, const
     return cudaGetLastError();
 }
 
+template <>
+cudaError_t launch_nonfinite<Real>(const StepArgs<Real>& a, unsigned long long* out, cudaStream_t st)
+{
+    nonfinite_kernel<Real><<<blocks_for(a.D, 256), 256, 0, st>>>(a, out);
+    return cudaGetLastError();
+}
+
 }  // namespace gpd

@@ -209,6 +209,12 @@ class BatchedSim:
         _lib.check(self.lib.gpd_episode_stats(self.h, out, int(clear), self._stream()))
         return np.array(list(out))
 
+    def count_nonfinite(self) -> int:
+        """Drones whose integrator state holds a NaN/Inf (failure detection; off the step path)."""
+        out = C.c_longlong(0)
+        _lib.check(self.lib.gpd_count_nonfinite(self.h, C.byref(out), self._stream()))
+        return int(out.value)
+
     @property
     def obs(self) -> torch.Tensor:
         return self.obs_buf[self._cur]

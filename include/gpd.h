@@ -201,6 +201,11 @@ int gpd_rollout_pid(gpd_sim* sim, int32_t n_ctrl_steps, const void* waypoints, i
 int gpd_grid_size(const gpd_sim* sim);
 int gpd_set_timeline_buffer(gpd_sim* sim, unsigned long long* dev_buf);
 
+/* Failure detection: number of drones whose position, quaternion, velocity or body rates hold a NaN/Inf (a DYN drone has
+ * no ground and no RPM clip for ActionType.RPM — BaseRLAviary.py:192 — so bad actions diverge without bound).
+ * Scans the persistent state; off the step path. Synchronises `stream`. */
+int gpd_count_nonfinite(gpd_sim* sim, long long* out_host, void* stream);
+
 /* Episode statistics kept on the device when auto_reset is on (what SB3's Monitor reports in the
  * single-process reference, examples/learn.py:53-57,142-146). out (host) = { episodes, sum_return, sum_length,
  * sum_return_sq, min_return, max_return, env_steps, terminated_episodes }. Synchronises `stream`.

@@ -771,3 +771,16 @@ def test_cuda_example_scripts_run():
     z_dw = downwash.run(num_envs=16, duration_sec=6)
     z_no = downwash.run(num_envs=16, duration_sec=6, physics=Physics.DYN)
     assert z_dw < z_no - 1e-4                         # the wake pushes the lower drone down
+
+
+def test_cuda_count_nonfinite():
+    kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="rpm", num_drones=1, pyb_freq=240, ctrl_freq=30,
+              physics_flags=0, init_xyz=None, init_rpy=None)
+    sim = make_sim(kw, num_envs=1000, precision="f32")
+    sim.reset()
+    assert sim.count_nonfinite() == 0
+    a = torch.zeros((1000, 1, 4), device="cuda")
+    a[7] = float("nan"); a[500, 0, 2] = float("inf")
+    sim.step(a)
+    assert sim.count_nonfinite() == 2
+    sim.close()
