@@ -236,22 +236,33 @@ def b200_arm(a):
         for k in range(tail):
             envs[k % nsets]._sim.step(acts[k])
     graph = tail_graph = None
-    if not a.no_graph:
+    graph_error = None
+
+    def capture():
         side = torch.cuda.Stream()
+        g_main, g_tail = torch.cuda.CUDAGraph(), None
         with torch.cuda.stream(side):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
+            with torch.cuda.graph(g_main, stream=side):
                 cycle()
             if tail:
                 saved = [(e._sim._cur, e._sim._have_prev) for e in envs]
-                tail_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(tail_graph, stream=side):
+                g_tail = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_tail, stream=side):
                     run_tail()
                 for e, (c, h) in zip(envs, saved):      # capture only records: restore the host-side ping-pong phase
                     e._sim._cur, e._sim._have_prev = c, h
         torch.cuda.synchronize()
-        graph.replay()
+        g_main.replay()
         torch.cuda.synchronize()
+        return g_main, g_tail
+
+    if not a.no_graph:
+        try:
+            graph, tail_graph = capture()
+        except Exception as ex:          # never lose the measurement to a capture problem: fall back to direct launches
+            graph = tail_graph = None
+            graph_error = repr(ex)[:200]
+            torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if graph is not None:           # bring the clocks to their loaded state before sampling starts
@@ -348,7 +359,7 @@ def b200_arm(a):
             "config": {"workload": workload_name(a), "envs_per_gpu": E, "substeps_per_step": S,
                        "l2": f"rotating {nsets} env sets per GPU (~{nsets * E * 700 / 1e6:.0f} MB touched per cycle > 126 MB L2)",
                        "launch": ("CUDA graph of %d step kernels x %d replays + %d-step tail graph" % (period, reps, tail))
-                       if graph is not None else "direct launches",
+                       if graph is not None else ("direct launches" + (f" (graph capture failed: {graph_error})" if graph_error else "")),
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "drone-substeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
