@@ -30,6 +30,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = {30: 646, 48: 934}      # SURVEY §8d, FP32, HoverAviary RPM KIN
+# FP64 mode: the 13-value state and the reward double; actions, ring and observation stay float32
+ALGO_BYTES_PER_ENV_STEP_F64 = {30: 646 + 2 * 52 + 4, 48: 934 + 2 * 52 + 4}
 METRIC = "drone-substeps/sec"
 
 
@@ -336,16 +338,14 @@ def b200_arm(a):
     if rank == 0:
         peak, peak_src = peaks()
         per_launch_ms = ms / K
-        algo = ALGO_BYTES_PER_ENV_STEP.get(a.ctrl_freq, None)
-        if a.precision == "f64" and algo:
-            algo = None
+        algo = (ALGO_BYTES_PER_ENV_STEP_F64 if a.precision == "f64" else ALGO_BYTES_PER_ENV_STEP).get(a.ctrl_freq, None)
         achieved = (algo * E / (per_launch_ms * 1e-3) / 1e9) if algo else None
         tr = traffic_from_profile()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_note": (tr or {}).get("note"),
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel<float,LEAN,N=1,VEC>",
+                "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel<%s,LEAN,N=1,VEC>" % ("double" if a.precision == "f64" else "float"),
                 "kernel_ms_per_launch": per_launch_ms}
         cpu = None
         if not a.no_cpu:
