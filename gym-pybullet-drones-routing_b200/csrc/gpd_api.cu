@@ -126,6 +126,7 @@ static void fill_drone(const gpd_drone_params& p, DevDrone<R>& d)
     d.KF_d = p.KF; d.KM_d = p.KM; d.GRAVITY_d = p.GRAVITY; d.L_d = p.L; d.ARM_d = p.L / std::sqrt(2.0);
     d.HOVER_RPM_d = p.HOVER_RPM; d.MAX_RPM_d = p.MAX_RPM;
     d.DT_INV_M = (R)0; d.DT_JINV[0] = d.DT_JINV[1] = d.DT_JINV[2] = (R)0;
+    d.DT_EULER[0] = d.DT_EULER[1] = d.DT_EULER[2] = (R)0;
 }
 
 template <typename R>
@@ -147,7 +148,7 @@ static size_t smem_bytes(bool f64, bool ctrl, bool multi, int DPB, int EPB)
     size_t stage = ctrl ? (size_t)DPB * 20 * rs : 0;
     size_t b = (stage + 15) & ~size_t(15);
     if (multi) b += (size_t)DPB * 4 * rs + (size_t)DPB * 2 * rs + (size_t)DPB * 4 + (size_t)EPB * 2 * 4;
-    b += 32;
+    b += 9 * 32;        // per-physics-warp statistics slots (float[4] + int[4] each)
     return (b + 15) & ~size_t(15);
 }
 
@@ -219,6 +220,8 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     fill_drone(c.drone, a.drone);
     a.drone.DT_INV_M = (R)((1.0 / c.pyb_freq) / c.drone.M);
     for (int k = 0; k < 3; ++k) a.drone.DT_JINV[k] = (R)((1.0 / c.pyb_freq) * c.drone.J_INV[k]);
+    for (int k = 0; k < 3; ++k)
+        a.drone.DT_EULER[k] = (R)((1.0 / c.pyb_freq) * c.drone.J_INV[k] * (c.drone.J[(k + 2) % 3] - c.drone.J[(k + 1) % 3]));
     fill_pid(c.pid, a.pid);
     int rc;
     V *sP, *sQ, *sV, *av, *rp; R* wz;

@@ -30,6 +30,7 @@ struct DevDrone {
     double KF_d, KM_d, GRAVITY_d, L_d, ARM_d, HOVER_RPM_d, MAX_RPM_d;
     R GRAVITY, MAX_RPM;
     R DT_INV_M, DT_JINV[3]; // FP32 mode: PYB_TIMESTEP/M and PYB_TIMESTEP*J^-1 (filled by gpd_create)
+    R DT_EULER[3];          // FP32 mode: PYB_TIMESTEP*J^-1[k]*(J[k+2]-J[k+1]), the gyroscopic coefficients of the diagonal J
     R J[3], JINV[3];
     R M, L, ARM;            // ARM = L/sqrt(2)  (BaseAviary.py:847-848)
     R KF, KM;

@@ -77,7 +77,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
 //   tile  : RL envs with A == 4: TMA box of the action history, DPB x (B-1) float4 (a.tma_bytes)
 //   stage : Ctrl env R[DPB*20] (state20 rows)
 //   MULTI : snap R[DPB*4] (x,y,z,-), red R[DPB*2], redi int[DPB], envf int[EPB*2]
-//   stats : float[4] + int[4]
+//   stats : per physics warp float[4] + int[4] (plain stores, combined by thread 0 after the block barrier)
 template <typename R>
 struct Smem {
     unsigned char* base;     // dynamic shared memory + the TMA history tile (tma_bytes, 128-byte multiple) that precedes everything
@@ -91,7 +91,7 @@ struct Smem {
     __device__ int* redi() const { return reinterpret_cast<int*>(red() + (multi ? size_t(DPB) * 2 : 0)); }
     __device__ int* envf() const { return redi() + (multi ? DPB : 0); }
     __device__ float* stat_f() const { return reinterpret_cast<float*>(envf() + (multi ? 2 * EPB : 0)); }
-    __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4); }
+    __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4 * 9); }     // up to 9 physics warps
 };
 
 __device__ __forceinline__ int float_to_ordered(float f)
@@ -305,8 +305,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool tma_copy = spec && a.use_tma;
     const bool edge_smem = tma_copy && VEC && a.tma_edge;       // physics threads read the two edge slots from shared memory
     if (tma_copy && t == nphys) mbar_init(&tma_bar, 1);
-    if (a.auto_reset && t < 4) { sm.stat_f()[t] = 0.f; sm.stat_i()[t] = (t == 2) ? 0x7fffffff : (t == 3 ? (int)0x80000000 : 0); }
-    if (a.auto_reset || edge_smem) __syncthreads();
+    if (edge_smem) __syncthreads();     // the physics threads will wait on the mbarrier the DMA lane just initialised
     pdl_wait();                         // everything above touched only parameters and shared memory
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
 
@@ -433,7 +432,16 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
 
     // ---- PYB_STEPS_PER_CTRL substeps (BaseAviary.py:343-372), state in registers ----
     R avx = R(0), avy = R(0), avz = R(0);
-    for (int sub = 0; sub < a.S; ++sub) {
+    int sub0 = 0;
+    if constexpr (LEAN && !M<R>::is_double) {       // all but the last substep: nothing but the state is needed
+        LeanStep c;
+        c.kt2 = (2.f * P.DT_INV_M) * F.Ttot; c.ktmg = P.DT_INV_M * F.T;
+        c.cx = P.DT_JINV[0] * F.tx; c.cy = P.DT_JINV[1] * F.ty; c.cz = P.DT_JINV[2] * F.tz;
+        c.ex = P.DT_EULER[0]; c.ey = P.DT_EULER[1]; c.ez = P.DT_EULER[2];
+        c.h = a.dt * .5f; c.hh = c.h * c.h;
+        for (; sub0 < a.S - 1; ++sub0) lean_substep_f32(a.dt, s, c);
+    }
+    for (int sub = sub0; sub < a.S; ++sub) {
         R m[9];
         const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);    // :836 (shared with the force models)
         const bool last = sub == a.S - 1;
@@ -554,26 +562,25 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         int el = cnt / a.S + 1;         // episode length in ctrl steps: the counter restarts with the episode
         const bool fin = lead && done;
         const unsigned m = __ballot_sync(0xffffffffu, fin);
-        if (m) {                        // reduce over the warp, then one set of shared-memory atomics per warp
-            float s1 = fin ? er : 0.f, s2 = fin ? er * er : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+        int nl = 0, nt = 0, mn = 0x7fffffff, mx = (int)0x80000000;
+        if (m) {                        // reduce the finished episodes of this warp
+            s1 = fin ? er : 0.f; s2 = fin ? er * er : 0.f;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 s1 += __shfl_xor_sync(0xffffffffu, s1, off);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, off);
             }
-            const int nl = __reduce_add_sync(0xffffffffu, fin ? el : 0);
-            const int nt = __popc(__ballot_sync(0xffffffffu, fin && term));
-            const int mn = __reduce_min_sync(0xffffffffu, fin ? float_to_ordered(er) : 0x7fffffff);
-            const int mx = __reduce_max_sync(0xffffffffu, fin ? float_to_ordered(er) : (int)0x80000000);
-            if ((t & 31) == 0) {
-                atomicAdd(&sm.stat_f()[0], s1);
-                atomicAdd(&sm.stat_f()[1], s2);
-                atomicAdd(&sm.stat_i()[0], __popc(m));
-                atomicAdd(&sm.stat_i()[1], nl);
-                atomicMin(&sm.stat_i()[2], mn);
-                atomicMax(&sm.stat_i()[3], mx);
-                if (nt) atomicAdd(&sm.stat_f()[2], (float)nt);
-            }
+            nl = __reduce_add_sync(0xffffffffu, fin ? el : 0);
+            nt = __popc(__ballot_sync(0xffffffffu, fin && term));
+            mn = __reduce_min_sync(0xffffffffu, fin ? float_to_ordered(er) : 0x7fffffff);
+            mx = __reduce_max_sync(0xffffffffu, fin ? float_to_ordered(er) : (int)0x80000000);
+        }
+        if ((t & 31) == 0) {            // every physics warp owns a slot: plain stores, no atomics, no initialisation pass
+            float* sf = sm.stat_f() + 4 * (t >> 5);
+            int* si = sm.stat_i() + 4 * (t >> 5);
+            sf[0] = s1; sf[1] = s2; sf[2] = (float)nt;
+            si[0] = __popc(m); si[1] = nl; si[2] = mn; si[3] = mx;
         }
         if (lead) a.p.ep_ret[e] = fin ? 0.f : er;
     }
@@ -653,17 +660,24 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         for (int idx = t; idx < rows * 20; idx += blockDim.x) out[idx] = st[idx];
     }
 
-    if (a.auto_reset && t == 0) {       // fold the block's partials into its own slot: RED (no return value, no wait)
+    if (a.auto_reset && t == 0) {       // combine the warps' partials, then RED (no return value, no wait) into this CTA's slot
         StatSlot* slot = a.p.stat_slots + blockIdx.x;
-        const int n = sm.stat_i()[0];
+        int n = 0, len = 0, mn = 0x7fffffff, mx = (int)0x80000000;
+        float sr = 0.f, sr2 = 0.f, st = 0.f;
+        for (int w = 0; w < (nphys >> 5); ++w) {
+            const float* sf = sm.stat_f() + 4 * w;
+            const int* si = sm.stat_i() + 4 * w;
+            n += si[0]; len += si[1]; mn = min(mn, si[2]); mx = max(mx, si[3]);
+            sr += sf[0]; sr2 += sf[1]; st += sf[2];
+        }
         if (n > 0) {
             atomicAdd(&slot->s[0], (double)n);
-            atomicAdd(&slot->s[1], (double)sm.stat_f()[0]);
-            atomicAdd(&slot->s[2], (double)sm.stat_i()[1]);
-            atomicAdd(&slot->s[3], (double)sm.stat_f()[1]);
-            atomicMin(&slot->mn, sm.stat_i()[2]);
-            atomicMax(&slot->mx, sm.stat_i()[3]);
-            if (sm.stat_f()[2] > 0.f) atomicAdd(&slot->s[5], (double)sm.stat_f()[2]);
+            atomicAdd(&slot->s[1], (double)sr);
+            atomicAdd(&slot->s[2], (double)len);
+            atomicAdd(&slot->s[3], (double)sr2);
+            atomicMin(&slot->mn, mn);
+            atomicMax(&slot->mx, mx);
+            if (st > 0.f) atomicAdd(&slot->s[5], (double)st);
         }
         atomicAdd(&slot->s[4], (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)blockIdx.x * a.EPB) : rows));
     }
