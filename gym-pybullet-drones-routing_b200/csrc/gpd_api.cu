@@ -334,37 +334,87 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     if (cfg->target_pos) memcpy(s->target_host.data(), cfg->target_pos, sizeof(double) * cfg->num_drones * 3);
     s->cfg.target_pos = nullptr;
     // Thread layout: P physics threads (one per drone, whole envs per block) + one DMA/copy warp for the RL envs.
-    int N = cfg->num_drones;
-    // default: 64 physics threads for single-drone envs (more, smaller CTAs balance better over 148 SMs), 128 otherwise
-    int P = cfg->threads_per_block ? cfg->threads_per_block : (N == 1 ? 64 : 128);
-    if (N == 1 && P > 128) P = 128;                       // register budget of the single-drone kernels
-    int DPB = P >= N ? (P / N) * N : N;
-    P = (DPB + 31) / 32 * 32;
-    int EPB = DPB / N;
-    const int copy = ctrl ? 0 : 32;
-    s->copy_threads = copy;
-    s->lc.threads = P + copy;
-    s->dpb = DPB;
-    s->lc.grid = (cfg->num_envs + EPB - 1) / EPB;
-    s->tma_ok = !ctrl && s->W % 4 == 0 && s->B >= 2 && DPB <= 256 && get_encode_fn() != nullptr &&
-                (A == 4 ? (s->B - 1) * 4 <= 256 : ((A * s->B) % 4 == 0 && A * s->B <= 256));
+    const int N = cfg->num_drones;
+    const bool tma_shape = !ctrl && s->W % 4 == 0 && s->B >= 2 && get_encode_fn() != nullptr &&
+                           (A == 4 ? (s->B - 1) * 4 <= 256 : ((A * s->B) % 4 == 0 && A * s->B <= 256));
+    bool tma_on = tma_shape;
+    int edge_req = -1;                                    // -1: automatic
     {
         const char* ev = getenv("GPD_TMA");
-        if (ev && atoi(ev) == 0) s->tma_ok = false;
+        if (ev && atoi(ev) == 0) tma_on = false;
+        ev = getenv("GPD_TMA_EDGE");
+        if (ev) edge_req = atoi(ev) ? 1 : 0;
     }
-    // whole-sector split of the row between the drone's thread and TMA (the two old slots the thread needs arrive through
-    // two extra 16-byte-wide TMA boxes): +10 % at >= 1 M drones (DRAM-bound), -2 % below ~256k drones (latency-bound: the
-    // physics threads then wait on the mbarrier and one more block barrier)
-    s->tma_edge = (s->tma_ok && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4 && s->D >= 262144) ? 1 : 0;
-    {
-        const char* ev = getenv("GPD_TMA_EDGE");
-        if (ev && atoi(ev) == 0) s->tma_edge = 0;
-        if (ev && atoi(ev) == 1 && s->tma_ok && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4) s->tma_edge = 1;
+    struct Layout { int P, DPB, EPB, threads, tma_edge, tma_bytes_box, tma_edge_bytes, tma_bytes; int64_t grid; size_t smem; };
+    auto make_layout = [&](int P) {
+        Layout L{};
+        if (N == 1 && P > 128) P = 128;                   // register budget of the single-drone kernels
+        L.DPB = P >= N ? (P / N) * N : N;
+        L.P = (L.DPB + 31) / 32 * 32;
+        L.EPB = L.DPB / N;
+        L.threads = L.P + (ctrl ? 0 : 32);
+        L.grid = (cfg->num_envs + L.EPB - 1) / L.EPB;
+        const bool tma = tma_on && L.DPB <= 256;
+        // whole-sector split of the row between the drone's thread and TMA (the two old slots the thread needs arrive
+        // through two extra 16-byte-wide TMA boxes): +10 % at >= 1 M drones (DRAM-bound), -2 % below ~256k drones
+        // (latency-bound: the physics threads then wait on the mbarrier and one more block barrier)
+        const bool edge_ok = tma && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4;
+        L.tma_edge = edge_ok && (edge_req < 0 ? s->D >= 262144 : edge_req == 1) ? 1 : 0;
+        L.tma_bytes_box = !tma ? 0 : (A == 4 ? L.DPB * (s->B - 1 - 2 * L.tma_edge) * 16 : L.DPB * A * s->B * 4);
+        L.tma_edge_bytes = L.tma_edge ? (L.DPB * 16 + 127) / 128 * 128 : 0;
+        L.tma_bytes = (L.tma_bytes_box + 127) / 128 * 128 + 2 * L.tma_edge_bytes;
+        L.smem = (size_t)L.tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, L.DPB, L.EPB);
+        return L;
+    };
+    // default: 64 physics threads for single-drone envs (more, smaller CTAs balance better over 148 SMs), 128 otherwise
+    Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : (N == 1 ? 64 : 128));
+    if (!cfg->threads_per_block) {
+        // Wave quantisation: a launch of 1..4 waves pays for its partly filled last wave (MultiHover x2 FP32 at 32,768
+        // envs: 512 CTAs on 444 slots = 28.5 us, 293 CTAs on 296 slots = 19.5 us).  Take the block size with the fewest
+        // waves, then the fullest last wave; the default wins ties.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        auto waves = [&](const Layout& l, double& fill) {
+            const int b = cfg->precision == GPD_F64
+                ? step_blocks_per_sm<double>(cfg->action_type, cfg->physics_flags, N, A, s->W, cfg->env_kind, l.threads, l.smem)
+                : step_blocks_per_sm<float>(cfg->action_type, cfg->physics_flags, N, A, s->W, cfg->env_kind, l.threads, l.smem);
+            if (b <= 0) { fill = 0; return (int64_t)1 << 40; }
+            const int64_t slots = (int64_t)b * sms, w = (l.grid + slots - 1) / slots;
+            fill = (double)l.grid / (double)(w * slots);
+            return w;
+        };
+        double fill0 = 0;
+        const int64_t w0 = waves(L, fill0);
+        if (w0 > 1 && w0 <= 4) {
+            int64_t wb = w0;
+            double fb = fill0;
+            for (int P = 32; P <= (N == 1 ? 128 : 256); P += 32) {
+                if (P < N) continue;
+                Layout c = make_layout(P);
+                double f = 0;
+                const int64_t w = waves(c, f);
+                if (getenv("GPD_DEBUG_LAYOUT"))
+                    fprintf(stderr, "[gpd]   candidate P=%d threads=%d smem=%zu grid=%lld waves=%lld fill=%.2f\n", c.P, c.threads, c.smem,
+                            (long long)c.grid, (long long)w, f);
+                if (w < wb || (w == wb && f > fb + 0.10)) { wb = w; fb = f; L = c; }
+            }
+        }
+        if (getenv("GPD_DEBUG_LAYOUT"))
+            fprintf(stderr, "[gpd] layout: %d physics threads, grid %lld, %lld wave(s) (default: %lld), smem %zu\n", L.P,
+                    (long long)L.grid, (long long)waves(L, fill0), (long long)w0, L.smem);
     }
-    s->tma_bytes_box = !s->tma_ok ? 0 : (A == 4 ? DPB * (s->B - 1 - 2 * s->tma_edge) * 16 : DPB * A * s->B * 4);
-    s->tma_edge_bytes = s->tma_edge ? (DPB * 16 + 127) / 128 * 128 : 0;
-    s->tma_bytes = (s->tma_bytes_box + 127) / 128 * 128 + 2 * s->tma_edge_bytes;
-    s->lc.smem = (size_t)s->tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, DPB, EPB);
+    const int DPB = L.DPB, EPB = L.EPB;
+    s->copy_threads = ctrl ? 0 : 32;
+    s->lc.threads = L.threads;
+    s->dpb = DPB;
+    s->lc.grid = L.grid;
+    s->tma_ok = tma_on && DPB <= 256;
+    s->tma_edge = L.tma_edge;
+    s->tma_bytes_box = L.tma_bytes_box;
+    s->tma_edge_bytes = L.tma_edge_bytes;
+    s->tma_bytes = L.tma_bytes;
+    s->lc.smem = L.smem;
+    (void)EPB;
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
         // parameter fetch overlap the previous kernel's tail); with a full wave the early-resident CTAs all issue their
         // loads at the same instant after the wait and the burst costs more than the overlap gains

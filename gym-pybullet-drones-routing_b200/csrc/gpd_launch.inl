@@ -5,16 +5,23 @@ namespace gpd {
 
 using Real = GPD_REAL;
 
+// The opt-in dynamic shared-memory limit of a step-kernel variant only ever grows (handles of different block sizes share it).
+template <bool LEAN, bool MULTI, bool VEC>
+static cudaError_t ensure_step_smem(size_t need)
+{
+    static size_t cur = 48 * 1024;
+    if (need <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<Real, LEAN, MULTI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e == cudaSuccess) cur = need;
+    return e;
+}
+
 template <bool LEAN, bool MULTI, bool VEC>
 static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, const CUtensorMap& tp, const CUtensorMap& to,
                                  const CUtensorMap& te, cudaStream_t st)
 {
-    static size_t smem_set = 48 * 1024;
-    if (lc.smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<Real, LEAN, MULTI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
-        if (e != cudaSuccess) return e;
-        smem_set = lc.smem;
-    }
+    cudaError_t e = ensure_step_smem<LEAN, MULTI, VEC>(lc.smem);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)lc.grid);
     cfg.blockDim = dim3((unsigned)lc.threads);
@@ -28,6 +35,46 @@ static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, c
     return cudaLaunchKernelEx(&cfg, step_kernel<Real, LEAN, MULTI, VEC>, a, tp, to, te);
 }
 
+static int step_variant(int action_type, int phy, int N, int A, int W, int env_kind)
+{
+    const bool rpm_like = action_type == GPD_ACT_RPM || action_type == GPD_ACT_ONE_D_RPM || action_type == GPD_ACT_CTRL_RPM;
+    const bool lean = rpm_like && phy == 0;
+    const bool multi = N > 1;
+    const bool vec = A == 4 && env_kind != GPD_ENV_CTRL && (W % 4 == 0);
+    return (lean ? 4 : 0) | (multi ? 2 : 0) | (vec ? 1 : 0);
+}
+
+template <bool LEAN, bool MULTI, bool VEC>
+static int occupancy_t(int threads, size_t smem)
+{
+    if (ensure_step_smem<LEAN, MULTI, VEC>(smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_kernel<Real, LEAN, MULTI, VEC>, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// Resident CTAs per SM of the step-kernel variant this configuration dispatches to (registers, threads, shared memory).
+template <>
+int step_blocks_per_sm<Real>(int action_type, int phy, int N, int A, int W, int env_kind, int threads, size_t smem)
+{
+    switch (step_variant(action_type, phy, N, A, W, env_kind)) {
+    case 0: return occupancy_t<false, false, false>(threads, smem);
+    case 1: return occupancy_t<false, false, true>(threads, smem);
+    case 2: return occupancy_t<false, true, false>(threads, smem);
+    case 3: return occupancy_t<false, true, true>(threads, smem);
+    case 4: return occupancy_t<true, false, false>(threads, smem);
+    case 5: return occupancy_t<true, false, true>(threads, smem);
+    case 6: return occupancy_t<true, true, false>(threads, smem);
+    default: return occupancy_t<true, true, true>(threads, smem);
+    }
+}
+
 template <>
 cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
                               const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st)
@@ -36,13 +83,7 @@ cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cons
     const CUtensorMap& tp = tm_prev ? *tm_prev : dummy;
     const CUtensorMap& to = tm_out ? *tm_out : dummy;
     const CUtensorMap& te = tm_edge ? *tm_edge : dummy;
-    const bool rpm_like = a.action_type == GPD_ACT_RPM || a.action_type == GPD_ACT_ONE_D_RPM ||
-                          a.action_type == GPD_ACT_CTRL_RPM;
-    const bool lean = rpm_like && a.phy == 0;
-    const bool multi = a.N > 1;
-    const bool vec = a.A == 4 && a.env_kind != GPD_ENV_CTRL && (a.W % 4 == 0);
-    const int key = (lean ? 4 : 0) | (multi ? 2 : 0) | (vec ? 1 : 0);
-    switch (key) {
+    switch (step_variant(a.action_type, a.phy, a.N, a.A, a.W, a.env_kind)) {
     case 0: return launch_step_t<false, false, false>(a, lc, tp, to, te, st);
     case 1: return launch_step_t<false, false, true>(a, lc, tp, to, te, st);
     case 2: return launch_step_t<false, true, false>(a, lc, tp, to, te, st);

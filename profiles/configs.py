@@ -55,6 +55,10 @@ def measure(make_env, make_action, nsets, reps, trials=3):
     sim = envs[0]._sim
     info = dict(E=sim.E, N=sim.N, S=sim.S, W=sim.W, us_per_step=best,
                 drone_substeps_per_s=sim.E * sim.N * sim.S / (best * 1e-6))
+    if getattr(envs[0], "AUTO_RESET", False) or getattr(sim, "auto_reset", False):
+        st = sim.episode_stats()         # include/gpd.h: episodes, sum return, sum length, sum return^2, min, max, env-steps, terminated
+        if st[6] > 0 and st[0] > 0:      # (each env set replays 2 action batches, so episodes are shorter than under fresh noise)
+            info.update(resets_per_env_step=st[0] / st[6], mean_episode_ctrl_steps=st[2] / st[0], mean_episode_return=st[1] / st[0])
     for e in envs:
         e.close()
     del envs, acts, gr
@@ -85,6 +89,43 @@ def c2_30():
                 lambda env, k: rand_act((E, 1, 4), k), nsets=8, reps=40)
     r.update(algo_bytes_per_env_step=646, workload="HoverAviary 65,536 envs RPM KIN FP32 240/30")
     return r
+
+
+def _c2_stream(label, make_action, **env_kw):
+    E = 65536
+    r = measure(lambda: HoverAviary(num_envs=E, ctrl_freq=30, precision="f32", auto_reset=True, **env_kw),
+                make_action, nsets=8, reps=40)
+    r.update(algo_bytes_per_env_step=646, workload="HoverAviary 65,536 envs RPM KIN FP32 240/30, " + label)
+    return r
+
+
+@config("c2_hover_30hz_f32_random_init")
+def c2_random_init():
+    """xyz ~ U([-1,1]^2 x [0.2,1.5]), rpy ~ U(-0.2,0.2)^3, uniform actions."""
+    E = 65536
+    rng = np.random.default_rng(0)
+    xyz = np.concatenate([rng.uniform(-1, 1, size=(E, 1, 2)), rng.uniform(0.2, 1.5, size=(E, 1, 1))], axis=-1)
+    rpy = rng.uniform(-0.2, 0.2, size=(E, 1, 3))
+    return _c2_stream("randomised initial poses", lambda env, k: rand_act((E, 1, 4), k), initial_xyzs=xyz, initial_rpys=rpy)
+
+
+@config("c2_hover_30hz_f32_near_hover")
+def c2_near_hover():
+    """a ~ N(0, 0.05^2) (longer episodes, still tilt-truncated)."""
+    E = 65536
+
+    def act(env, k):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(k)
+        return torch.randn((E, 1, 4), generator=g, device="cuda") * 0.05
+    return _c2_stream("near-hover actions N(0, 0.05^2)", act)
+
+
+@config("c2_hover_30hz_f32_symmetric")
+def c2_symmetric():
+    """all four motors equal -- the only stream that reaches the 8 s time limit."""
+    E = 65536
+    return _c2_stream("symmetric actions (four equal motors)", lambda env, k: rand_act((E, 1, 1), k, -0.05, 0.05).expand(E, 1, 4).contiguous())
 
 
 @config("c2_hover_48hz_f32")
