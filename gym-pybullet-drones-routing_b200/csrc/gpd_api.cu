@@ -345,16 +345,19 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         ev = getenv("GPD_TMA_EDGE");
         if (ev) edge_req = atoi(ev) ? 1 : 0;
     }
-    struct Layout { int P, DPB, EPB, threads, tma_edge, tma_bytes_box, tma_edge_bytes, tma_bytes; int64_t grid; size_t smem; };
+    struct Layout { int P, DPB, EPB, threads, copy, tma_edge, tma_bytes_box, tma_edge_bytes, tma_bytes; int64_t grid; size_t smem; };
     auto make_layout = [&](int P) {
         Layout L{};
         if (N == 1 && P > 128) P = 128;                   // register budget of the single-drone kernels
         L.DPB = P >= N ? (P / N) * N : N;
         L.P = (L.DPB + 31) / 32 * 32;
         L.EPB = L.DPB / N;
-        L.threads = L.P + (ctrl ? 0 : 32);
+        // the FP64 multi-drone kernels are built for at most 256 threads (128 registers, two CTAs per SM): envs of more than
+        // 224 drones run without the DMA warp there (the whole block shares the history copy)
+        L.copy = (ctrl || (cfg->precision == GPD_F64 && N > 1 && L.P + 32 > 256)) ? 0 : 32;
+        L.threads = L.P + L.copy;
         L.grid = (cfg->num_envs + L.EPB - 1) / L.EPB;
-        const bool tma = tma_on && L.DPB <= 256;
+        const bool tma = tma_on && L.DPB <= 256 && L.copy > 0;
         // whole-sector split of the row between the drone's thread and TMA (the two old slots the thread needs arrive
         // through two extra 16-byte-wide TMA boxes): +10 % at >= 1 M drones (DRAM-bound), -2 % below ~256k drones
         // (latency-bound: the physics threads then wait on the mbarrier and one more block barrier)
@@ -404,11 +407,11 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
                     (long long)L.grid, (long long)waves(L, fill0), (long long)w0, L.smem);
     }
     const int DPB = L.DPB, EPB = L.EPB;
-    s->copy_threads = ctrl ? 0 : 32;
+    s->copy_threads = L.copy;
     s->lc.threads = L.threads;
     s->dpb = DPB;
     s->lc.grid = L.grid;
-    s->tma_ok = tma_on && DPB <= 256;
+    s->tma_ok = tma_on && DPB <= 256 && L.copy > 0;
     s->tma_edge = L.tma_edge;
     s->tma_bytes_box = L.tma_bytes_box;
     s->tma_edge_bytes = L.tma_edge_bytes;

@@ -432,6 +432,7 @@ def test_cuda_vec_env_protocol():
     ("ONE_D_RPM (A=1, scalar rows)", dict(action_type="one_d_rpm"), 70, 30),
     ("DYN+DRAG single drone", dict(physics_flags=2), 70, 30),
     ("DYN+GND+DRAG+DW, 5 drones", dict(env_kind="multihover", num_drones=5, physics_flags=7), 21, 30),
+    ("240 drones per RL env: FP64 block without the DMA warp", dict(env_kind="multihover", num_drones=240), 3, 10),
 ])
 def test_cuda_f64_edge_shapes_vs_oracle(desc, kw_over, E, steps):
     """Ragged / extreme shapes: every code path of the step kernel (TMA and register history copy, all block tails)
