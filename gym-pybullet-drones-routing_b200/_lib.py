@@ -14,7 +14,8 @@ import numpy as np
 from .params import DroneParams, PIDParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgpd_b200.so")
+# GPD_B200_LIB points at another build of the same C ABI (kernel A/B experiments); the default is the in-tree library
+LIB_PATH = os.environ.get("GPD_B200_LIB") or os.path.join(_HERE, "lib", "libgpd_b200.so")
 
 GPD_F32, GPD_F64 = 0, 1
 ACT_CODES = {"rpm": 0, "pid": 1, "vel": 2, "one_d_rpm": 3, "one_d_pid": 4, "ctrl_rpm": 5, "ctrl_vel": 6}

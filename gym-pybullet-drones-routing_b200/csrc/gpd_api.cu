@@ -369,12 +369,20 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         L.smem = (size_t)L.tma_bytes + smem_bytes(cfg->precision == GPD_F64, ctrl, N > 1, L.DPB, L.EPB);
         return L;
     };
-    // default: 64 physics threads for single-drone envs (more, smaller CTAs balance better over 148 SMs), 128 otherwise
-    Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : (N == 1 ? 64 : 128));
+    // defaults (measured, profiles/README.md): 64 physics threads for the lean FP32 single-drone kernel (64 registers: more,
+    // smaller CTAs balance better over 148 SMs) and for A < 4, 128 for the other single-drone kernels; multi-drone envs
+    // 224 (+ the DMA warp = 256), 128 with downwash
+    const bool f64 = cfg->precision == GPD_F64;
+    const bool rpm_like = cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_ONE_D_RPM || cfg->action_type == GPD_ACT_CTRL_RPM;
+    const bool lean = rpm_like && cfg->physics_flags == 0;
+    int P0 = 64;
+    if (N == 1) P0 = (A == 4 && (f64 || !lean)) ? 128 : 64;      // A < 4: the 32 funnel-copy lanes limit the tile to 64 rows
+    else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 128 : 224;    // downwash: a block barrier per substep favours smaller CTAs
+    Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0);
     if (!cfg->threads_per_block) {
         // Wave quantisation: a launch of 1..4 waves pays for its partly filled last wave (MultiHover x2 FP32 at 32,768
         // envs: 512 CTAs on 444 slots = 28.5 us, 293 CTAs on 296 slots = 19.5 us).  Take the block size with the fewest
-        // waves, then the fullest last wave; the default wins ties.
+        // waves; the default wins ties.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
         auto waves = [&](const Layout& l, double& fill) {
@@ -391,7 +399,7 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         if (w0 > 1 && w0 <= 4) {
             int64_t wb = w0;
             double fb = fill0;
-            for (int P = 32; P <= (N == 1 ? 128 : 256); P += 32) {
+            for (int P = 64; P <= (N == 1 ? 128 : 256); P += 32) {      // 32-thread CTAs always lose (measured)
                 if (P < N) continue;
                 Layout c = make_layout(P);
                 double f = 0;
@@ -399,7 +407,7 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
                 if (getenv("GPD_DEBUG_LAYOUT"))
                     fprintf(stderr, "[gpd]   candidate P=%d threads=%d smem=%zu grid=%lld waves=%lld fill=%.2f\n", c.P, c.threads, c.smem,
                             (long long)c.grid, (long long)w, f);
-                if (w < wb || (w == wb && f > fb + 0.10)) { wb = w; fb = f; L = c; }
+                if (w < wb) { wb = w; fb = f; L = c; }
             }
         }
         if (getenv("GPD_DEBUG_LAYOUT"))

@@ -276,8 +276,10 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
 //   VEC   : A == 4 (observation rows are float4-granular)
 // ============================================================================================
 template <typename R, bool LEAN, bool MULTI, bool VEC>
-// FP64 multi-drone: 128 registers (two 256-thread CTAs per SM) beat 168 registers without spills by 1.2-1.4x (C3, C4)
-__global__ void __launch_bounds__(MULTI ? (sizeof(R) == 8 ? 256 : 288) : 160, MULTI ? (sizeof(R) == 8 ? 2 : 1) : (sizeof(R) == 4 ? (LEAN ? 6 : 4) : 2))
+// FP64: occupancy beats spill-free code.  Multi-drone: 128 registers (two 256-thread CTAs per SM) instead of 168 is 1.2-1.4x
+// faster (C3, C4); single-drone: 96 registers (four 160-thread CTAs) instead of 141-168 is 1.1-1.26x faster (65,536 .. 1 M envs);
+// 80 registers lose again (measured, profiles/README.md).
+__global__ void __launch_bounds__(MULTI ? (sizeof(R) == 8 ? 256 : 288) : 160, MULTI ? (sizeof(R) == 8 ? 2 : 1) : (sizeof(R) == 4 ? (LEAN ? 6 : 4) : 4))
 step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUtensorMap tm_prev,
             const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_edge)
 {
