@@ -785,3 +785,35 @@ def test_cuda_count_nonfinite():
     sim.step(a)
     assert sim.count_nonfinite() == 2
     sim.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("N,flags,act", [(1, 0, "rpm"), (1, 3, "rpm"), (3, 7, "rpm"), (1, 0, "pid")])
+def test_cuda_block_size_does_not_change_results(precision, N, flags, act):
+    """The block size (threads_per_block, or the occupancy-aware default of gpd_create) is a pure scheduling choice:
+    every layout must give bit-identical observations, rewards, flags and state, with auto-reset on."""
+    rng = np.random.default_rng(5)
+    E = 517
+    xyz = np.stack([rng.uniform(-.5, .5, (E, N)), rng.uniform(-.5, .5, (E, N)), rng.uniform(0.05, 1.0, (E, N))], -1)
+    kw = dict(model=DroneModel.CF2X, env_kind="hover" if N == 1 else "multihover", action_type=act, num_drones=N, pyb_freq=240,
+              ctrl_freq=48 if act == "pid" else 30, physics_flags=flags, init_xyz=xyz, init_rpy=rng.uniform(-.2, .2, (E, N, 3)))
+    A = 3 if act == "pid" else 4
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (E, N, A)).astype(np.float32)).cuda() for _ in range(25)]
+    outs = []
+    for tpb in (0, 32, 96, 128, 224, 256):
+        sim = make_sim(kw, num_envs=E, precision=precision, auto_reset=True, tpb=tpb)
+        sim.reset()
+        rec = []
+        for a in acts:
+            o, r, te, tr = sim.step(a)
+            rec.append((o.clone(), r.clone(), te.clone(), tr.clone()))
+        st, rr, ps, cnt = sim.get_state()
+        outs.append((rec, st.clone(), rr.clone(), cnt.clone(), sim.episode_stats()))
+        sim.close()
+    ref = outs[0]
+    for o in outs[1:]:
+        for (a0, a1, a2, a3), (b0, b1, b2, b3) in zip(ref[0], o[0]):
+            assert torch.equal(a0, b0) and torch.equal(a1, b1) and torch.equal(a2, b2) and torch.equal(a3, b3)
+        assert torch.equal(ref[1], o[1]) and torch.equal(ref[2], o[2]) and torch.equal(ref[3], o[3])
+        assert ref[4][0] == o[4][0] and ref[4][2] == o[4][2] and ref[4][6] == o[4][6]      # episodes, lengths, env-steps
+        assert abs(ref[4][1] - o[4][1]) <= 1e-6 * max(1.0, abs(ref[4][1]))                # sum of returns (FP32 partial sums)
