@@ -817,3 +817,61 @@ def test_cuda_block_size_does_not_change_results(precision, N, flags, act):
         assert torch.equal(ref[1], o[1]) and torch.equal(ref[2], o[2]) and torch.equal(ref[3], o[3])
         assert ref[4][0] == o[4][0] and ref[4][2] == o[4][2] and ref[4][6] == o[4][6]      # episodes, lengths, env-steps
         assert abs(ref[4][1] - o[4][1]) <= 1e-6 * max(1.0, abs(ref[4][1]))                # sum of returns (FP32 partial sums)
+
+
+@pytest.mark.parametrize("name", ["c3_multihover2_gnd_drag_f64", "c4_ctrl64_dw_f64", "c4_ctrl64_dw_f32", "c5_hover_pid_f32"])
+def test_cuda_full_size_properties_other_configs(name):
+    """BASELINE.json configs 3-5 at their full sizes, through size-independent properties: (1) determinism,
+    (2) env-permutation equivariance, (3) a sample of envs against the FP64 oracle fed the same actions."""
+    rng = np.random.default_rng(11)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    hover = load_drone_params(DroneModel.CF2X).HOVER_RPM
+    if name.startswith("c3"):
+        E, N, A, T, prec, ns, tol = 32768, 2, 4, 12, "f64", 128, 1e-9
+        xyz, rpy = _random_init(rng, E, N)
+        kw = dict(model=DroneModel.CF2X, env_kind="multihover", action_type="rpm", num_drones=N, pyb_freq=240, ctrl_freq=30,
+                  physics_flags=3, init_xyz=xyz, init_rpy=rpy)
+        acts = [(torch.rand((E, N, A), generator=g, device="cuda") * 2 - 1) for _ in range(T)]
+    elif name.startswith("c4"):
+        prec = name[-3:]
+        # FP32 tolerance: the 64-drone downwash field is stiff (dF/dz = 2F/dz at dz = 0.045 m), rounding differences grow ~10x per
+        # 5 ctrl steps; measured 7.6e-4
+        E, N, A, T, ns, tol = 4096, 64, 4, 5, 6, (1e-9 if prec == "f64" else 2e-3)
+        # FP64 uses the BASELINE box; FP32 gives every drone of an env its own height, 0.045 m apart in a random order: the
+        # downwash model is singular at dz -> 0+ (alpha ~ 1/dz^2, DESIGN 3.4) and amplifies any rounding difference there
+        z = (rng.uniform(0.2, 3, (E, N, 1)) if prec == "f64"
+             else 0.2 + 0.045 * np.argsort(rng.random((E, N)), axis=1)[..., None].astype(np.float64))
+        xyz = np.concatenate([rng.uniform(-2, 2, (E, N, 2)), z], -1)
+        rpy = np.zeros((E, N, 3))
+        kw = dict(model=DroneModel.CF2X, env_kind="ctrl", action_type="ctrl_rpm", num_drones=N, pyb_freq=240, ctrl_freq=48,
+                  physics_flags=4, init_xyz=xyz, init_rpy=rpy)
+        dt = torch.float64 if prec == "f64" else torch.float32
+        acts = [(hover * (1 + 0.02 * (torch.rand((E, N, A), generator=g, device="cuda", dtype=torch.float64) * 2 - 1))).to(dt)
+                for _ in range(T)]
+    else:
+        E, N, A, T, prec, ns, tol = 2097152, 1, 3, 6, "f32", 256, 1e-4
+        xyz, rpy = _random_init(rng, E, N)
+        kw = dict(model=DroneModel.CF2X, env_kind="hover", action_type="pid", num_drones=N, pyb_freq=240, ctrl_freq=48,
+                  physics_flags=0, init_xyz=xyz, init_rpy=rpy)
+        acts = [(torch.rand((E, N, A), generator=g, device="cuda") * 2 - 1) for _ in range(T)]
+    perm = torch.randperm(E, generator=g, device="cuda")
+    p = perm.cpu().numpy()
+    sims = [make_sim(kw, E, prec), make_sim(kw, E, prec), make_sim(dict(kw, init_xyz=xyz[p], init_rpy=rpy[p]), E, prec)]
+    sample = np.sort(rng.choice(E, ns, replace=False))
+    ref = make_oracle(dict(kw, init_xyz=xyz[sample], init_rpy=rpy[sample]), num_envs=ns)
+    for s in sims:
+        s.reset()
+    worst = 0.0
+    for t in range(T):
+        oa, ra, ta, tra = sims[0].step(acts[t])
+        ob, rb, tb, trb = sims[1].step(acts[t])
+        op, rp, tp, trp = sims[2].step(acts[t][perm].contiguous())
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(tra, trb)      # (1)
+        assert torch.equal(oa[perm], op) and torch.equal(ra[perm], rp) and torch.equal(tra[perm], trp)            # (2)
+        ref.step(acts[t][sample].cpu().numpy())
+        st = sims[0].get_state()[0].double().cpu().numpy()[sample]
+        worst = max(worst, rel_err(st[..., S_POS], ref.state20[..., S_POS]), rel_err(st[..., S_VEL], ref.state20[..., S_VEL]))
+    assert worst <= tol, worst                                                                                    # (3)
+    assert sims[0].count_nonfinite() == 0
+    for s in sims:
+        s.close()
