@@ -359,10 +359,11 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         L.grid = (cfg->num_envs + L.EPB - 1) / L.EPB;
         const bool tma = tma_on && L.DPB <= 256 && L.copy > 0;
         // whole-sector split of the row between the drone's thread and TMA (the two old slots the thread needs arrive
-        // through two extra 16-byte-wide TMA boxes): +10 % at >= 1 M drones (DRAM-bound), -2 % below ~256k drones
-        // (latency-bound: the physics threads then wait on the mbarrier and one more block barrier)
+        // through two extra 16-byte-wide TMA boxes): no read-modify-write of half-written sectors in ECC HBM.  Measured
+        // +10 % at >= 1 M drones, +4 % at 131,072, +2 % at 65,536, -3 % at <= 32,768 (latency-bound: the physics threads
+        // then wait on the mbarrier and one more block barrier)
         const bool edge_ok = tma && A == 4 && (s->W / 4) % 2 == 0 && s->B >= 4;
-        L.tma_edge = edge_ok && (edge_req < 0 ? s->D >= 262144 : edge_req == 1) ? 1 : 0;
+        L.tma_edge = edge_ok && (edge_req < 0 ? s->D >= 65536 : edge_req == 1) ? 1 : 0;
         L.tma_bytes_box = !tma ? 0 : (A == 4 ? L.DPB * (s->B - 1 - 2 * L.tma_edge) * 16 : L.DPB * A * s->B * 4);
         L.tma_edge_bytes = L.tma_edge ? (L.DPB * 16 + 127) / 128 * 128 : 0;
         L.tma_bytes = (L.tma_bytes_box + 127) / 128 * 128 + 2 * L.tma_edge_bytes;
