@@ -399,7 +399,6 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         const int64_t w0 = waves(L, fill0);
         if (w0 > 1 && w0 <= 4) {
             int64_t wb = w0;
-            double fb = fill0;
             for (int P = 64; P <= (N == 1 ? 128 : 256); P += 32) {      // 32-thread CTAs always lose (measured)
                 if (P < N) continue;
                 Layout c = make_layout(P);
@@ -408,7 +407,7 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
                 if (getenv("GPD_DEBUG_LAYOUT"))
                     fprintf(stderr, "[gpd]   candidate P=%d threads=%d smem=%zu grid=%lld waves=%lld fill=%.2f\n", c.P, c.threads, c.smem,
                             (long long)c.grid, (long long)w, f);
-                if (w < wb) { wb = w; fb = f; L = c; }
+                if (w < wb) { wb = w; L = c; }
             }
         }
         if (getenv("GPD_DEBUG_LAYOUT"))

@@ -113,19 +113,22 @@ __device__ __forceinline__ void write_shifted_from_smem(const float4* __restrict
                                                         int ct, int CT)
 {
     const int W4 = W >> 2, H4 = (A * B) >> 2, keep = A * (B - 1);
+    const int ktail = keep >> 2;                      // first float4 of a row that holds a float of the new slot
     const float* actb = act + row0 * A;
     float4* out4 = reinterpret_cast<float4*>(out) + row0 * W4 + 3;
-    const int total = rows * H4;
-    for (int idx = ct; idx < total; idx += CT) {
-        const int row = idx / H4, k = idx - row * H4;
-        const float4 lo = tile[row * H4 + k];
-        const float4 hi = (k + 1 < H4) ? tile[row * H4 + k + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // (row, k) advance by CT float4s per iteration without a division in the loop
+    int row = ct / H4, k = ct - row * H4;
+    const int dq = CT / H4, dr = CT - dq * H4;
+    while (row < rows) {
+        const float4* src = tile + row * H4 + k;
+        const float4 lo = src[0];
+        const float4 hi = (k + 1 < H4) ? src[1] : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 v;
         if (A == 1) v = make_float4(lo.y, lo.z, lo.w, hi.x);
         else if (A == 2) v = make_float4(lo.z, lo.w, hi.x, hi.y);
         else v = make_float4(lo.w, hi.x, hi.y, hi.z);
-        const int c = 4 * k;
-        if (c + 3 >= keep) {
+        if (k >= ktail) {
+            const int c = 4 * k;
             const float* ar = actb + row * A;
             if (c + 0 >= keep) v.x = __ldg(ar + (c + 0 - keep));
             if (c + 1 >= keep) v.y = __ldg(ar + (c + 1 - keep));
@@ -133,6 +136,8 @@ __device__ __forceinline__ void write_shifted_from_smem(const float4* __restrict
             if (c + 3 >= keep) v.w = __ldg(ar + (c + 3 - keep));
         }
         out4[row * W4 + k] = v;
+        k += dr; row += dq;
+        if (k >= H4) { k -= H4; ++row; }
     }
 }
 
@@ -693,7 +698,7 @@ template <typename R, bool VEC>
 __global__ void __launch_bounds__(288)
 reset_kernel(const __grid_constant__ StepArgs<R> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const bool ctrl = a.env_kind == GPD_ENV_CTRL;
     Smem<R> sm{ smem_raw + a.tma_bytes, a.DPB, a.EPB, ctrl, false };
     const int t = threadIdx.x;
