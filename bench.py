@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--sets", type=int, default=8, help="independent env sets rotated to defeat L2 residency")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--tpb", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=1,
+                    help="async env pools: env set j always steps on stream j %% STREAMS, so independent sets overlap (default 1 = "
+                         "every step ordered on one stream, the headline mode)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -222,9 +225,32 @@ def b200_arm(a):
         e.reset()
     period = 2 * nsets
 
+    nstreams = max(1, min(a.streams, nsets))
+    pool = [torch.cuda.Stream(device=dev) for _ in range(nstreams - 1)]
+
+    def run_steps(n):
+        if nstreams == 1:
+            for k in range(n):
+                envs[k % nsets]._sim.step(acts[k])
+            return
+        # fork: every pool stream waits for the caller's stream; set j always runs on stream j % nstreams (its own steps stay
+        # ordered); join: the caller's stream waits for every pool stream.  All of it is capturable.
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in pool:
+            st.wait_event(fork)
+        for k in range(n):
+            j = (k % nsets) % nstreams
+            with torch.cuda.stream(main if j == 0 else pool[j - 1]):
+                envs[k % nsets]._sim.step(acts[k])
+        for st in pool:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
     def cycle():
-        for k in range(period):
-            envs[k % nsets]._sim.step(acts[k])
+        run_steps(period)
 
     # warm-up (also touches every buffer)
     wu = max(3, a.warmup)
@@ -235,8 +261,7 @@ def b200_arm(a):
     reps, tail = divmod(K, period)          # EXACTLY K steps: `reps` replays of the 16-step graph + one tail graph
 
     def run_tail():
-        for k in range(tail):
-            envs[k % nsets]._sim.step(acts[k])
+        run_steps(tail)
     graph = tail_graph = None
     graph_error = None
 
@@ -347,6 +372,9 @@ def b200_arm(a):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel<%s,LEAN,N=1,VEC>" % ("double" if a.precision == "f64" else "float"),
                 "kernel_ms_per_launch": per_launch_ms}
+        if nstreams > 1:
+            roof["note"] = (f"{nstreams} streams: launches of independent env sets overlap, so kernel_ms_per_launch is the "
+                            "throughput-equivalent time per launch, not one launch's duration")
         cpu = None
         if not a.no_cpu:
             r = cpu_run(a, seconds=a.cpu_seconds)
@@ -360,6 +388,7 @@ def b200_arm(a):
                        "l2": f"rotating {nsets} env sets per GPU (~{nsets * E * 700 / 1e6:.0f} MB touched per cycle > 126 MB L2)",
                        "launch": ("CUDA graph of %d step kernels x %d replays + %d-step tail graph" % (period, reps, tail))
                        if graph is not None else ("direct launches" + (f" (graph capture failed: {graph_error})" if graph_error else "")),
+                       "streams": nstreams,
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "drone-substeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

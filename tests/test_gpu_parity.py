@@ -875,3 +875,33 @@ def test_cuda_full_size_properties_other_configs(name):
     assert sims[0].count_nonfinite() == 0
     for s in sims:
         s.close()
+
+
+@pytest.mark.parametrize("extra", [[], ["--streams", "2"], ["--no-graph"], ["--steps", "37"]])
+def test_cuda_bench_contract_line(extra):
+    """bench.py (product arm) on a small workload: ONE JSON line with the agreed keys, exactly K launches, a live roofline."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--steps", "64", "--warmup", "4", "--envs", "4096", "--sets", "2",
+           "--e2e-steps", "3", "--cpu-seconds", "0.5"] + extra
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    K = 37 if "--steps" in extra else 64
+    for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"]:
+        assert k in d, k
+    assert d["metric"] == "drone-substeps/sec" and d["steps"] == K and d["gpu_launches"] == K and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f32" and "workload" in d["config"]
+    assert d["episode_stats"]["env_steps"] >= 4096 * K              # every timed launch stepped every env (warm-up on top)
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - 646 * 4096 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 16 and d["e2e"]["d2h_bytes_per_step"] == 4096 * (72 * 4 + 6)
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["config"]["streams"] == (2 if "--streams" in extra else 1)
