@@ -905,3 +905,35 @@ def test_cuda_bench_contract_line(extra):
     assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 16 and d["e2e"]["d2h_bytes_per_step"] == 4096 * (72 * 4 + 6)
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["config"]["streams"] == (2 if "--streams" in extra else 1)
+
+
+def test_cuda_async_env_pools_match_sequential_stepping():
+    """AsyncEnvPools: pools stepping on their own streams give exactly the results of stepping them one after the other."""
+    from gpd_b200.envs import HoverAviary
+    from gpd_b200.pool import AsyncEnvPools
+    E, T, P = 3000, 12, 3
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    acts = [[torch.rand((E, 1, 4), generator=g, device="cuda") * 2 - 1 for _ in range(P)] for _ in range(T)]
+    seq = [HoverAviary(num_envs=E, precision="f32", auto_reset=True) for _ in range(P)]
+    pools = AsyncEnvPools([HoverAviary(num_envs=E, precision="f32", auto_reset=True) for _ in range(P)])
+    for e in seq:
+        e.reset()
+    obs0 = pools.reset()
+    assert all(torch.equal(o, e._sim.obs) for o, e in zip(obs0, seq))
+    for t in range(T):
+        ref = [tuple(x.clone() for x in e._sim.step(a)) for e, a in zip(seq, acts[t])]
+        if t % 2:
+            out = pools.step_all(acts[t])
+        else:                                  # interleaved use: launch all, consume in reverse order
+            for j in range(P):
+                pools.step_async(j, acts[t][j])
+            out = [None] * P
+            for j in reversed(range(P)):
+                out[j] = pools.wait(j)
+        for r, o in zip(ref, out):
+            assert all(torch.equal(a, b) for a, b in zip(r, o))
+    with pytest.raises(RuntimeError):
+        pools.wait(0)
+    pools.close()
+    for e in seq:
+        e.close()
