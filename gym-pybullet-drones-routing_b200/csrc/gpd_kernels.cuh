@@ -440,6 +440,10 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
 
     // ---- PYB_STEPS_PER_CTRL substeps (BaseAviary.py:343-372), state in registers ----
     R avx = R(0), avy = R(0), avz = R(0);
+    R wsum_prev = R(0), wsum_cur = R(0);            // _drag's sum of rotor speeds (:773): constant over the substeps
+    if constexpr (!LEAN) {
+        if (a.phy & GPD_PHY_DRAG) { wsum_prev = drag_wsum(rpm_prev); wsum_cur = drag_wsum(rpm_r); }
+    }
     int sub0 = 0;
     if constexpr (LEAN && !M<R>::is_double) {       // all but the last substep: nothing but the state is needed
         LeanStep c;
@@ -460,25 +464,20 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             const R* pg = nullptr;
             const R* pb = nullptr;
             if (a.phy & GPD_PHY_GND) {
-                R roll, pitch, yaw;
-                if constexpr (M<R>::is_double) {
-                    quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw); // snapshot rpy, :346-347,518
-                } else {
-                    // FP32 throughput mode: the gate |roll|,|pitch| < pi/2 (BaseAviary.py:742) only needs the signs of the
-                    // atan2/asin arguments: |atan2(y,x)| < pi/2 <=> x > 0 (or x = y = 0); |asin(s)| < pi/2 <=> |s| < 1, and
-                    // Bullet's gimbal branch (|s| >= 0.99999) returns pitch = +-pi/2, which fails the gate.
-                    const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
-                    const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
-                    const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
-                    roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
-                    pitch = gimbal ? R(GPD_PI) : R(0);
-                    yaw = R(0);
-                }
+                // The gate |roll|,|pitch| < pi/2 of the rpy snapshot (BaseAviary.py:346-347,518,742) needs only the signs of
+                // the atan2/asin arguments: |atan2(y,x)| < pi/2 <=> x > 0 (or x = y = 0); Bullet's gimbal branch
+                // (|s| >= 0.99999) returns pitch = +-pi/2 and fails the gate, otherwise |asin(s)| < pi/2.  Exact in both
+                // precisions up to atan2 results that ROUND to pi/2 (|y/x| > 1e16): three libm calls per substep saved.
+                const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
+                const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
+                const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
+                const R roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
+                const R pitch = gimbal ? R(GPD_PI) : R(0);
                 if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
             }
             if (a.phy & GPD_PHY_DRAG) {                          // :359,366: rpm = last_clipped_action
                 R db[3];
-                drag_body(P, sub == 0 ? rpm_prev : rpm_r, m, s.vx, s.vy, s.vz, db);
+                drag_body_w(P, sub == 0 ? wsum_prev : wsum_cur, m, s.vx, s.vy, s.vz, db);
                 fb[0] += db[0]; fb[1] += db[1]; fb[2] += db[2];
                 pb = fb;
             }

@@ -227,17 +227,28 @@ __device__ __forceinline__ bool ground_effect(const DevDrone<R>& P, const R rpm[
     return M<R>::abs(roll) < R(GPD_PI / 2) && M<R>::abs(pitch) < R(GPD_PI / 2);            // :742
 }
 
-// BaseAviary._drag (BaseAviary.py:754-781): CoM LINK-frame (body) force.
+// BaseAviary._drag (BaseAviary.py:754-781): CoM LINK-frame (body) force.  wsum = sum of the rotor speeds in rad/s (:773).
 template <typename R>
-__device__ __forceinline__ void drag_body(const DevDrone<R>& P, const R rpm_prev[4], const R* m, R vx, R vy, R vz, R out[3])
+__device__ __forceinline__ R drag_wsum(const R rpm_prev[4])
 {
     R w0 = R(2) * R(GPD_PI) * rpm_prev[0] / R(60), w1 = R(2) * R(GPD_PI) * rpm_prev[1] / R(60);
     R w2 = R(2) * R(GPD_PI) * rpm_prev[2] / R(60), w3 = R(2) * R(GPD_PI) * rpm_prev[3] / R(60);
-    R wsum = w0 + ((w1 + w2) + w3);                                                        // :773
+    return w0 + ((w1 + w2) + w3);
+}
+
+template <typename R>
+__device__ __forceinline__ void drag_body_w(const DevDrone<R>& P, R wsum, const R* m, R vx, R vy, R vz, R out[3])
+{
     R fx = (R(-1) * P.DRAG[0] * wsum) * vx, fy = (R(-1) * P.DRAG[1] * wsum) * vy, fz = (R(-1) * P.DRAG[2] * wsum) * vz;
     out[0] = (m[0] * fx + m[3] * fy) + m[6] * fz;                                          // :774 base_rot.T · (...)
     out[1] = (m[1] * fx + m[4] * fy) + m[7] * fz;
     out[2] = (m[2] * fx + m[5] * fy) + m[8] * fz;
+}
+
+template <typename R>
+__device__ __forceinline__ void drag_body(const DevDrone<R>& P, const R rpm_prev[4], const R* m, R vx, R vy, R vz, R out[3])
+{
+    drag_body_w(P, drag_wsum(rpm_prev), m, vx, vy, vz, out);
 }
 
 // One pair term of BaseAviary._downwash (BaseAviary.py:799-804): body-z force on "me" from a drone at (ox,oy,oz).
