@@ -41,6 +41,7 @@ template <> struct M<float> {
     static __device__ __forceinline__ float asin(float x) { return fast_atan2f(x, sqrtf(fmaxf(0.f, (1.f - x) * (1.f + x)))); }
     static __device__ __forceinline__ float exp(float x) { return expf(x); }
     static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }      // MUFU.RCP, 2 ulp
     static __device__ __forceinline__ float4 make4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
 };
 template <> struct M<double> {
@@ -51,6 +52,7 @@ template <> struct M<double> {
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double abs(double x) { return fabs(x); }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
     static __device__ __forceinline__ double4 make4(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
 };
 
@@ -221,7 +223,7 @@ __device__ __forceinline__ bool ground_effect(const DevDrone<R>& P, const R rpm[
     for (int k = 0; k < 4; ++k) {
         R h = pz + (m[6] * P.ROTOR[k][0] + m[7] * P.ROTOR[k][1] + m[8] * P.ROTOR[k][2]);   // :732-739
         if (h < P.GND_EFF_H_CLIP) h = P.GND_EFF_H_CLIP;                                    // :740
-        R ratio = P.PROP_RADIUS / (R(4) * h);
+        R ratio = M<R>::div(P.PROP_RADIUS, R(4) * h);                                      // h >= GND_EFF_H_CLIP > 0
         out[k] = rpm[k] * rpm[k] * P.KF * P.GND_EFF_COEFF * (ratio * ratio);               // :741
     }
     return M<R>::abs(roll) < R(GPD_PI / 2) && M<R>::abs(pitch) < R(GPD_PI / 2);            // :742
