@@ -110,6 +110,9 @@ struct LaunchCfg {
 };
 
 // implemented once per precision in gpd_f32.cu / gpd_f64.cu
+// step-kernel code variants (template axis KIND of gpd::step_kernel)
+enum { GPD_K_FORCES = 0, GPD_K_LEAN = 1, GPD_K_PID = 2 };
+
 template <typename R> int step_blocks_per_sm(int action_type, int phy, int N, int A, int W, int env_kind, int threads, size_t smem);
 template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
                                               const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st);

@@ -276,18 +276,22 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
 
 // ============================================================================================
 // The fused step kernel: BaseAviary.step (BaseAviary.py:259-383).
-//   LEAN  : plain Physics.DYN with an RPM-type action (no controller, no force models)
+//   KIND  : which optional code the variant carries (each keeps its own register budget)
+//             GPD_K_LEAN   plain Physics.DYN with an RPM-type action (no controller, no force models)
+//             GPD_K_FORCES RPM-type action with ground effect / drag / downwash
+//             GPD_K_PID    DSLPID in the loop (PID / VEL / ONE_D_PID / CTRL_VEL actions), force models optional
 //   MULTI : N > 1 (per-env reductions / downwash need block-level exchange)
 //   VEC   : A == 4 (observation rows are float4-granular)
 // ============================================================================================
-template <typename R, bool LEAN, bool MULTI, bool VEC>
+template <typename R, int KIND, bool MULTI, bool VEC>
 // FP64: occupancy beats spill-free code.  Multi-drone: 128 registers (two 256-thread CTAs per SM) instead of 168 is 1.2-1.4x
 // faster (C3, C4); single-drone: 96 registers (four 160-thread CTAs) instead of 141-168 is 1.1-1.26x faster (65,536 .. 1 M envs);
 // 80 registers lose again (measured, profiles/README.md).
-__global__ void __launch_bounds__(MULTI ? (sizeof(R) == 8 ? 256 : 288) : 160, MULTI ? (sizeof(R) == 8 ? 2 : 1) : (sizeof(R) == 4 ? (LEAN ? 6 : 4) : 4))
+__global__ void __launch_bounds__(MULTI ? (sizeof(R) == 8 ? 256 : 288) : 160, MULTI ? (sizeof(R) == 8 ? 2 : 1) : (sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 6 : (KIND == GPD_K_PID ? 5 : 4)) : 4))
 step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUtensorMap tm_prev,
             const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_edge)
 {
+    constexpr bool LEAN = KIND == GPD_K_LEAN, HAS_PID = KIND == GPD_K_PID;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t tma_bar;
     const bool ctrl = a.env_kind == GPD_ENV_CTRL;
@@ -381,7 +385,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             rpm[0] = clip(v.x, R(0), P.MAX_RPM); rpm[1] = clip(v.y, R(0), P.MAX_RPM);
             rpm[2] = clip(v.z, R(0), P.MAX_RPM); rpm[3] = clip(v.w, R(0), P.MAX_RPM);
         } else if (a.action_type == GPD_ACT_CTRL_VEL) {
-            if constexpr (!LEAN) {                               // VelocityAviary.py:129-170, in the action's own precision
+            if constexpr (HAS_PID) {                             // VelocityAviary.py:129-170, in the action's own precision
                 V4<R> v = reinterpret_cast<const V4<R>*>(a.actions)[d];
                 R n = M<R>::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
                 R u0 = R(0), u1 = R(0), u2 = R(0);
@@ -424,7 +428,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         double v = P.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[0]));                             // :225
         rpm[0] = rpm[1] = rpm[2] = rpm[3] = v;
     }
-    if constexpr (!LEAN) {
+    if constexpr (HAS_PID) {
         if (a.action_type == GPD_ACT_PID || a.action_type == GPD_ACT_VEL || a.action_type == GPD_ACT_ONE_D_PID) {
             if (active) {
                 R r4[4];

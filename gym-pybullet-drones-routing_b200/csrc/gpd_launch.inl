@@ -6,21 +6,21 @@ namespace gpd {
 using Real = GPD_REAL;
 
 // The opt-in dynamic shared-memory limit of a step-kernel variant only ever grows (handles of different block sizes share it).
-template <bool LEAN, bool MULTI, bool VEC>
+template <int KIND, bool MULTI, bool VEC>
 static cudaError_t ensure_step_smem(size_t need)
 {
     static size_t cur = 48 * 1024;
     if (need <= cur) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<Real, LEAN, MULTI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<Real, KIND, MULTI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
     if (e == cudaSuccess) cur = need;
     return e;
 }
 
-template <bool LEAN, bool MULTI, bool VEC>
+template <int KIND, bool MULTI, bool VEC>
 static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, const CUtensorMap& tp, const CUtensorMap& to,
                                  const CUtensorMap& te, cudaStream_t st)
 {
-    cudaError_t e = ensure_step_smem<LEAN, MULTI, VEC>(lc.smem);
+    cudaError_t e = ensure_step_smem<KIND, MULTI, VEC>(lc.smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)lc.grid);
@@ -32,27 +32,27 @@ static cudaError_t launch_step_t(const StepArgs<Real>& a, const LaunchCfg& lc, c
     attr[0].val.programmaticStreamSerializationAllowed = lc.pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, step_kernel<Real, LEAN, MULTI, VEC>, a, tp, to, te);
+    return cudaLaunchKernelEx(&cfg, step_kernel<Real, KIND, MULTI, VEC>, a, tp, to, te);
 }
 
 static int step_variant(int action_type, int phy, int N, int A, int W, int env_kind)
 {
     const bool rpm_like = action_type == GPD_ACT_RPM || action_type == GPD_ACT_ONE_D_RPM || action_type == GPD_ACT_CTRL_RPM;
-    const bool lean = rpm_like && phy == 0;
+    const int kind = !rpm_like ? GPD_K_PID : (phy == 0 ? GPD_K_LEAN : GPD_K_FORCES);
     const bool multi = N > 1;
     const bool vec = A == 4 && env_kind != GPD_ENV_CTRL && (W % 4 == 0);
-    return (lean ? 4 : 0) | (multi ? 2 : 0) | (vec ? 1 : 0);
+    return kind * 4 + (multi ? 2 : 0) + (vec ? 1 : 0);
 }
 
-template <bool LEAN, bool MULTI, bool VEC>
+template <int KIND, bool MULTI, bool VEC>
 static int occupancy_t(int threads, size_t smem)
 {
-    if (ensure_step_smem<LEAN, MULTI, VEC>(smem) != cudaSuccess) {
+    if (ensure_step_smem<KIND, MULTI, VEC>(smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_kernel<Real, LEAN, MULTI, VEC>, threads, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_kernel<Real, KIND, MULTI, VEC>, threads, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -64,14 +64,19 @@ template <>
 int step_blocks_per_sm<Real>(int action_type, int phy, int N, int A, int W, int env_kind, int threads, size_t smem)
 {
     switch (step_variant(action_type, phy, N, A, W, env_kind)) {
-    case 0: return occupancy_t<false, false, false>(threads, smem);
-    case 1: return occupancy_t<false, false, true>(threads, smem);
-    case 2: return occupancy_t<false, true, false>(threads, smem);
-    case 3: return occupancy_t<false, true, true>(threads, smem);
-    case 4: return occupancy_t<true, false, false>(threads, smem);
-    case 5: return occupancy_t<true, false, true>(threads, smem);
-    case 6: return occupancy_t<true, true, false>(threads, smem);
-    default: return occupancy_t<true, true, true>(threads, smem);
+    case 0: return occupancy_t<GPD_K_FORCES, false, false>(threads, smem);
+    case 1: return occupancy_t<GPD_K_FORCES, false, true>(threads, smem);
+    case 2: return occupancy_t<GPD_K_FORCES, true, false>(threads, smem);
+    case 3: return occupancy_t<GPD_K_FORCES, true, true>(threads, smem);
+    case 4: return occupancy_t<GPD_K_LEAN, false, false>(threads, smem);
+    case 5: return occupancy_t<GPD_K_LEAN, false, true>(threads, smem);
+    case 6: return occupancy_t<GPD_K_LEAN, true, false>(threads, smem);
+    case 7: return occupancy_t<GPD_K_LEAN, true, true>(threads, smem);
+    case 8: return occupancy_t<GPD_K_PID, false, false>(threads, smem);
+    case 9: return occupancy_t<GPD_K_PID, false, true>(threads, smem);
+    case 10: return occupancy_t<GPD_K_PID, true, false>(threads, smem);
+    case 11: return occupancy_t<GPD_K_PID, true, true>(threads, smem);
+    default: return 0;
     }
 }
 
@@ -84,14 +89,19 @@ cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cons
     const CUtensorMap& to = tm_out ? *tm_out : dummy;
     const CUtensorMap& te = tm_edge ? *tm_edge : dummy;
     switch (step_variant(a.action_type, a.phy, a.N, a.A, a.W, a.env_kind)) {
-    case 0: return launch_step_t<false, false, false>(a, lc, tp, to, te, st);
-    case 1: return launch_step_t<false, false, true>(a, lc, tp, to, te, st);
-    case 2: return launch_step_t<false, true, false>(a, lc, tp, to, te, st);
-    case 3: return launch_step_t<false, true, true>(a, lc, tp, to, te, st);
-    case 4: return launch_step_t<true, false, false>(a, lc, tp, to, te, st);
-    case 5: return launch_step_t<true, false, true>(a, lc, tp, to, te, st);
-    case 6: return launch_step_t<true, true, false>(a, lc, tp, to, te, st);
-    default: return launch_step_t<true, true, true>(a, lc, tp, to, te, st);
+    case 0: return launch_step_t<GPD_K_FORCES, false, false>(a, lc, tp, to, te, st);
+    case 1: return launch_step_t<GPD_K_FORCES, false, true>(a, lc, tp, to, te, st);
+    case 2: return launch_step_t<GPD_K_FORCES, true, false>(a, lc, tp, to, te, st);
+    case 3: return launch_step_t<GPD_K_FORCES, true, true>(a, lc, tp, to, te, st);
+    case 4: return launch_step_t<GPD_K_LEAN, false, false>(a, lc, tp, to, te, st);
+    case 5: return launch_step_t<GPD_K_LEAN, false, true>(a, lc, tp, to, te, st);
+    case 6: return launch_step_t<GPD_K_LEAN, true, false>(a, lc, tp, to, te, st);
+    case 7: return launch_step_t<GPD_K_LEAN, true, true>(a, lc, tp, to, te, st);
+    case 8: return launch_step_t<GPD_K_PID, false, false>(a, lc, tp, to, te, st);
+    case 9: return launch_step_t<GPD_K_PID, false, true>(a, lc, tp, to, te, st);
+    case 10: return launch_step_t<GPD_K_PID, true, false>(a, lc, tp, to, te, st);
+    case 11: return launch_step_t<GPD_K_PID, true, true>(a, lc, tp, to, te, st);
+    default: return cudaErrorInvalidValue;
     }
 }
 
