@@ -83,6 +83,9 @@ class BatchedSim:
                                  if self.auto_reset and not self.is_ctrl else None)
         self._cur = 0
         self._have_prev = False
+        # the step path re-uses these ctypes pointers (the buffers never move): eager stepping is host-bound at 65k envs
+        self._p_obs = [_ptr(b) for b in self.obs_buf]
+        self._p_out = (_ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), _ptr(self.terminal_kin))
         if init_xyz is not None or init_rpy is not None:
             self.set_init_poses(init_xyz, init_rpy)
             self.reset()
@@ -121,10 +124,10 @@ class BatchedSim:
         if actions.numel() != self.E * self.N * self.A:
             raise ValueError(f"actions must have {self.E}x{self.N}x{self.A} elements, got {tuple(actions.shape)}")
         nxt = self._cur ^ 1
-        prev = self.obs_buf[self._cur] if self._have_prev else None
-        _lib.check(self.lib.gpd_step(self.h, _ptr(actions), _ptr(prev), _ptr(self.obs_buf[nxt]), _ptr(self.reward),
-                                     _ptr(self.terminated), _ptr(self.truncated), _ptr(self.terminal_kin),
-                                     self._stream()))
+        rc = self.lib.gpd_step(self.h, C.c_void_p(actions.data_ptr()), self._p_obs[self._cur] if self._have_prev else None,
+                               self._p_obs[nxt], *self._p_out, self._stream())
+        if rc:
+            _lib.check(rc)
         self._cur, self._have_prev = nxt, True
         return self.obs_buf[nxt], self.reward, self.terminated, self.truncated
 
