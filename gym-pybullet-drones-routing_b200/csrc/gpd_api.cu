@@ -63,6 +63,7 @@ struct gpd_sim {
     LaunchCfg lc;
     int dpb = 0;
     int copy_threads = 0;
+    const void* last_obs = nullptr;   // the observation buffer most recently written by gpd_step / gpd_reset (device)
     std::vector<void*> allocs;
     StepArgs<float> a32;
     StepArgs<double> a64;
@@ -232,6 +233,9 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     if ((rc = dev_alloc(s, &av, (size_t)s->D))) return rc;
     if ((rc = dev_alloc(s, &rp, (size_t)s->D))) return rc;
     a.p.sP = sP; a.p.sQ = sQ; a.p.sV = sV; a.p.sWz = wz; a.p.aux_av = av; a.p.aux_rpm = rp;
+    int32_t* auth;
+    if ((rc = dev_alloc(s, &auth, (size_t)1))) return rc;
+    a.p.aux_auth = auth;
     const bool pidfam = c.action_type == GPD_ACT_PID || c.action_type == GPD_ACT_VEL || c.action_type == GPD_ACT_ONE_D_PID;
     R* pid = nullptr;
     if ((rc = dev_alloc(s, &pid, (size_t)s->D * 9))) return rc;      // also used by gpd_rollout_pid
@@ -266,6 +270,10 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     {
         const char* ev = getenv("GPD_PDL_EARLY");
         a.pdl_trigger_early = ev ? atoi(ev) : (s->lc.grid <= 296 ? 1 : 0);
+        // lean FP32 KIN sims keep ang_v / last_clipped_action only in the observation row (32 B per drone-step less to write)
+        const bool rpm_act = c.action_type == GPD_ACT_RPM || c.action_type == GPD_ACT_ONE_D_RPM;
+        ev = getenv("GPD_AUX_ALWAYS");
+        a.skip_aux = (sizeof(R) == 4 && rpm_act && c.physics_flags == 0 && c.env_kind != GPD_ENV_CTRL && !(ev && atoi(ev))) ? 1 : 0;
     }
     a.tma_edge_bytes = s->tma_edge_bytes;
     a.use_tma = 0;
@@ -480,6 +488,7 @@ int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* o
         a.reset_mask = env_mask; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out;
         CU(launch_reset<float>(a, s->lc, st));
     }
+    if (obs_out) s->last_obs = obs_out;
     return GPD_OK;
 }
 
@@ -512,6 +521,7 @@ int gpd_step(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_ou
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
         CU(launch_step<float>(a, s->lc, tp, to, te, st));
     }
+    s->last_obs = obs_out;
     return GPD_OK;
 }
 
@@ -604,9 +614,9 @@ int gpd_get_state(gpd_sim* s, void* state20, void* rpy_rates, void* pid_state, i
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     CU(cudaSetDevice(s->cfg.device));
     if (s->cfg.precision == GPD_F64)
-        CU(launch_get_state<double>(s->a64, (double*)state20, (double*)rpy_rates, (double*)pid_state, step_counter, (cudaStream_t)stream));
+        CU(launch_get_state<double>(s->a64, (const float*)s->last_obs, (double*)state20, (double*)rpy_rates, (double*)pid_state, step_counter, (cudaStream_t)stream));
     else
-        CU(launch_get_state<float>(s->a32, (float*)state20, (float*)rpy_rates, (float*)pid_state, step_counter, (cudaStream_t)stream));
+        CU(launch_get_state<float>(s->a32, (const float*)s->last_obs, (float*)state20, (float*)rpy_rates, (float*)pid_state, step_counter, (cudaStream_t)stream));
     return GPD_OK;
 }
 

@@ -51,7 +51,9 @@ struct DevPid {
 
 // Persistent per-drone state, SoA of 16-byte vectors (D = E*N drones):
 //   sP = (pos.x, pos.y, pos.z, rates.x)   sQ = quat xyzw   sV = (vel.x, vel.y, vel.z, rates.y)   sWz = rates.z
-//   aux_av = (ang_v.xyz, 0), aux_rpm = last_clipped_action   (outputs kept so gpd_get_state is exact)
+//   aux_av = (ang_v.xyz, 0), aux_rpm = last_clipped_action   (outputs kept so gpd_get_state is exact).
+//   Lean FP32 KIN sims (StepArgs::skip_aux) do not write them per step: both are bit-exact functions of the observation
+//   row (kin[9..11]; newest ring slot + counter) and are re-derived on demand; *aux_auth says which copy is authoritative.
 //   pid[k*D + d], k = 0..8
 template <typename R>
 struct SimPtrs {
@@ -61,6 +63,7 @@ struct SimPtrs {
     R* sWz;
     typename Vec4<R>::type* aux_av;
     typename Vec4<R>::type* aux_rpm;
+    int32_t* aux_auth;      // [1] 1 = the aux arrays are authoritative (after reset-all / gpd_set_state), 0 = derive from the obs row
     R* pid;
     int32_t* counter;       // [E] BaseAviary.step_counter
     float* ep_ret;          // [E] running episode return (auto_reset only)
@@ -83,6 +86,7 @@ struct StepArgs {
     int32_t use_tma;        // history moved by TMA tensor copies (needs obs_prev and float4-granular rows)
     int32_t tma_bytes;      // shared-memory bytes reserved for the TMA tile (multiple of 128)
     int32_t tma_bytes_box;  // bytes one TMA box transfers: DPB * (B-1-2*tma_edge) * 16
+    int32_t skip_aux;          // lean FP32 KIN sims: ang_v / last_clipped_action live in the observation row, not in aux_*
     int32_t pdl_trigger_early; // PDL: release the dependent launch at CTA start (small grids) or after this CTA's stores
     int32_t tma_edge_bytes; // shared-memory bytes of one edge box (DPB*16 rounded up to 128)
     int32_t tma_edge;       // 1: rows are 32-byte aligned, the box skips the first and last shifted slot (written by the drone's thread)
@@ -117,7 +121,7 @@ template <typename R> int step_blocks_per_sm(int action_type, int phy, int N, in
 template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
                                               const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st);
 template <typename R> cudaError_t launch_reset(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
-template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, R* state20, R* rpy_rates, R* pid_state,
+template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, const float* obs_latest, R* state20, R* rpy_rates, R* pid_state,
                                                    int32_t* counter, cudaStream_t st);
 template <typename R> cudaError_t launch_set_state(const StepArgs<R>& a, const R* state20, const R* rpy_rates,
                                                    const R* pid_state, const int32_t* counter, cudaStream_t st);

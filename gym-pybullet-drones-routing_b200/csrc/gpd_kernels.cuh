@@ -230,6 +230,27 @@ __device__ __forceinline__ void store_state(const SimPtrs<R>& p, int64_t d, cons
     p.sWz[d] = s.wz;
 }
 
+// Lean FP32 KIN sims: ang_v and last_clipped_action re-derived from an observation row (float32 kin[9..11]; newest ring
+// slot through the action map of BaseRLAviary.py:192,225 — bit-identical to what the step computed; zero right after a
+// reset, i.e. while the env's step counter is 0, BaseAviary.py:468).
+template <typename R>
+__device__ __forceinline__ void derive_aux(const StepArgs<R>& a, const float* __restrict__ obs, int64_t d, int64_t e,
+                                           R av[3], R rpm[4])
+{
+    const float* row = obs + d * a.W;
+    av[0] = (R)row[9]; av[1] = (R)row[10]; av[2] = (R)row[11];
+    rpm[0] = rpm[1] = rpm[2] = rpm[3] = R(0);
+    if (a.p.counter[e] != 0) {
+        const float* act = row + a.W - a.A;
+        if (a.action_type == GPD_ACT_RPM) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rpm[k] = (R)(a.drone.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[k])));
+        } else if (a.action_type == GPD_ACT_ONE_D_RPM) {
+            rpm[0] = rpm[1] = rpm[2] = rpm[3] = (R)(a.drone.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[0])));
+        }
+    }
+}
+
 template <typename R>
 __device__ __forceinline__ void init_state(const StepArgs<R>& a, int64_t d, int i, State<R>& s)
 {
@@ -623,8 +644,12 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     if (active) {
         if (i == 0) a.p.counter[e] = (a.auto_reset && done) ? 0 : cnt + a.S;   // BaseAviary.py:382
         store_state(a.p, d, s);
-        a.p.aux_av[d] = M<R>::make4(avx, avy, avz, R(0));
-        a.p.aux_rpm[d] = M<R>::make4(out_rpm[0], out_rpm[1], out_rpm[2], out_rpm[3]);
+        if (!(LEAN && a.skip_aux)) {    // lean FP32 KIN sims: both live in the observation row written below (derive_aux)
+            a.p.aux_av[d] = M<R>::make4(avx, avy, avz, R(0));
+            a.p.aux_rpm[d] = M<R>::make4(out_rpm[0], out_rpm[1], out_rpm[2], out_rpm[3]);
+        } else if (d == 0) {
+            *a.p.aux_auth = 0;
+        }
     }
 
     // ---- stage this drone's observation row in shared memory ----
@@ -731,11 +756,18 @@ reset_kernel(const __grid_constant__ StepArgs<R> a)
                 a.p.counter[e] = 0;
                 if (a.p.ep_ret) a.p.ep_ret[e] = 0.f;
             }
+            if (d == 0 && a.reset_mask == nullptr) *a.p.aux_auth = 1;     // everything was reset: the (zero) arrays are exact
         } else {
             load_state(a.p, d, s);
-            V4<R> av = a.p.aux_av[d], rp = a.p.aux_rpm[d];
-            avx = av.x; avy = av.y; avz = av.z;
-            rpm[0] = rp.x; rpm[1] = rp.y; rpm[2] = rp.z; rpm[3] = rp.w;
+            if (a.skip_aux && a.obs_prev && *a.p.aux_auth == 0) {
+                R av3[3];
+                derive_aux(a, a.obs_prev, d, e, av3, rpm);
+                avx = av3[0]; avy = av3[1]; avz = av3[2];
+            } else {
+                V4<R> av = a.p.aux_av[d], rp = a.p.aux_rpm[d];
+                avx = av.x; avy = av.y; avz = av.z;
+                rpm[0] = rp.x; rpm[1] = rp.y; rpm[2] = rp.z; rpm[3] = rp.w;
+            }
         }
     }
     if (!a.obs_out) return;
@@ -770,8 +802,8 @@ reset_kernel(const __grid_constant__ StepArgs<R> a)
 
 // ---- state export / import (BaseAviary._getDroneStateVector, BaseAviary.py:541-561) ----
 template <typename R>
-__global__ void get_state_kernel(const StepArgs<R> a, R* __restrict__ state20, R* __restrict__ rpy_rates,
-                                 R* __restrict__ pid_state, int32_t* __restrict__ counter)
+__global__ void get_state_kernel(const StepArgs<R> a, const float* __restrict__ obs_latest, R* __restrict__ state20,
+                                 R* __restrict__ rpy_rates, R* __restrict__ pid_state, int32_t* __restrict__ counter)
 {
     int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d < a.E && counter) counter[d] = a.p.counter[d];
@@ -781,7 +813,14 @@ __global__ void get_state_kernel(const StepArgs<R> a, R* __restrict__ state20, R
     if (state20) {
         R roll, pitch, yaw;
         quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
-        V4<R> av = a.p.aux_av[d], rp = a.p.aux_rpm[d];
+        V4<R> av, rp;
+        if (a.skip_aux && obs_latest && *a.p.aux_auth == 0) {
+            R av3[3], r4[4];
+            derive_aux(a, obs_latest, d, d / a.N, av3, r4);
+            av = M<R>::make4(av3[0], av3[1], av3[2], R(0)); rp = M<R>::make4(r4[0], r4[1], r4[2], r4[3]);
+        } else {
+            av = a.p.aux_av[d]; rp = a.p.aux_rpm[d];
+        }
         R* r = state20 + d * 20;
         r[0] = s.px; r[1] = s.py; r[2] = s.pz; r[3] = s.qx; r[4] = s.qy; r[5] = s.qz; r[6] = s.qw;
         r[7] = roll; r[8] = pitch; r[9] = yaw; r[10] = s.vx; r[11] = s.vy; r[12] = s.vz;
@@ -807,6 +846,7 @@ __global__ void set_state_kernel(const StepArgs<R> a, const R* __restrict__ stat
         s.vx = r[10]; s.vy = r[11]; s.vz = r[12];
         a.p.aux_av[d] = M<R>::make4(r[13], r[14], r[15], R(0));
         a.p.aux_rpm[d] = M<R>::make4(r[16], r[17], r[18], r[19]);
+        if (d == 0) *a.p.aux_auth = 1;      // every drone's ang_v / last_clipped_action was just written
     }
     if (rpy_rates) { s.wx = rpy_rates[d * 3]; s.wy = rpy_rates[d * 3 + 1]; s.wz = rpy_rates[d * 3 + 2]; }
     store_state(a.p, d, s);

@@ -124,10 +124,10 @@ cudaError_t launch_reset<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cud
 static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 template <>
-cudaError_t launch_get_state<Real>(const StepArgs<Real>& a, Real* state20, Real* rpy_rates, Real* pid_state,
-                                   int32_t* counter, cudaStream_t st)
+cudaError_t launch_get_state<Real>(const StepArgs<Real>& a, const float* obs_latest, Real* state20, Real* rpy_rates,
+                                   Real* pid_state, int32_t* counter, cudaStream_t st)
 {
-    get_state_kernel<Real><<<blocks_for(a.D, 128), 128, 0, st>>>(a, state20, rpy_rates, pid_state, counter);
+    get_state_kernel<Real><<<blocks_for(a.D, 128), 128, 0, st>>>(a, obs_latest, state20, rpy_rates, pid_state, counter);
     return cudaGetLastError();
 }
 

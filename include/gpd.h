@@ -162,7 +162,10 @@ int gpd_reset_host(gpd_sim* sim, const uint8_t* env_mask, void* obs_out, void* s
  *   rpy_rates dev [E][N][3] Real (BaseAviary.py:477,874); pid_state dev [E][N][9] Real: integral_pos_e3,
  *   integral_rpy_e3, last_rpy3 (DSLPIDControl.py:73-78); step_counter dev [E] int32. Any pointer may be NULL.
  * gpd_set_state reads pos, quat, vel, ang_v, last_clipped_action from state20 (rpy is derived). Together they
- * checkpoint/resume a simulation bit-exactly. */
+ * checkpoint/resume a simulation bit-exactly.
+ * FP32 KIN sims with an RPM-type action and no force model keep ang_v and last_clipped_action only in the observation
+ * row: gpd_get_state (and a masked gpd_reset) re-derive them, bit-exactly, from the observation buffer most recently
+ * passed as obs_out - the same buffer the next gpd_step needs intact as obs_prev. */
 int gpd_get_state(gpd_sim* sim, void* state20, void* rpy_rates, void* pid_state, int32_t* step_counter, void* stream);
 int gpd_set_state(gpd_sim* sim, const void* state20, const void* rpy_rates, const void* pid_state,
                   const int32_t* step_counter, void* stream);

@@ -937,3 +937,52 @@ def test_cuda_async_env_pools_match_sequential_stepping():
     pools.close()
     for e in seq:
         e.close()
+
+
+@pytest.mark.parametrize("act,N", [("rpm", 1), ("one_d_rpm", 1), ("rpm", 3)])
+def test_cuda_f32_lean_state_export_matches_explicit_aux_arrays(act, N, monkeypatch):
+    """Lean FP32 KIN sims do not write ang_v / last_clipped_action per step: gpd_get_state re-derives them from the
+    observation row.  A twin sim built with GPD_AUX_ALWAYS=1 (arrays written every step) must export bit-identical
+    state through steps, auto-resets, masked resets, set_state and the host path."""
+    rng = np.random.default_rng(9)
+    E = 700
+    xyz, rpy = _random_init(rng, E, N)
+    kw = dict(model=DroneModel.CF2X, env_kind="hover" if N == 1 else "multihover", action_type=act, num_drones=N, pyb_freq=240,
+              ctrl_freq=30, physics_flags=0, init_xyz=xyz, init_rpy=rpy)
+    A = 4 if act == "rpm" else 1
+    lean = make_sim(kw, E, "f32", auto_reset=True)
+    monkeypatch.setenv("GPD_AUX_ALWAYS", "1")
+    twin = make_sim(kw, E, "f32", auto_reset=True)
+    monkeypatch.delenv("GPD_AUX_ALWAYS")
+
+    def same():
+        a, b = lean.get_state(), twin.get_state()
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        return a
+    lean.reset(); twin.reset()
+    same()
+    nonzero = False
+    for t in range(30):
+        a = torch.from_numpy(rng.uniform(-1, 1, (E, N, A)).astype(np.float32)).cuda()
+        if t == 17:                            # host-buffer path in the middle of the run
+            ol = lean.step_host(a.cpu().numpy()); ot = twin.step_host(a.cpu().numpy())
+            assert all(np.array_equal(x, y) for x, y in zip(ol[:4], ot[:4]))
+        else:
+            ol, ot = lean.step(a), twin.step(a)
+            assert all(torch.equal(x, y) for x, y in zip(ol, ot))
+        st = same()
+        nonzero |= bool((st[0][..., 16:20] != 0).any()) and bool((st[0][..., 13:16] != 0).any())
+        if t == 9:                             # masked reset: untouched envs keep ang_v / rpm, reset ones read zero
+            mask = torch.from_numpy((rng.random(E) < 0.3).astype(np.uint8)).cuda()
+            assert torch.equal(lean.reset(mask), twin.reset(mask))
+            st = same()
+            m = mask.bool().cpu()
+            assert (st[0].cpu()[m][..., 13:20] == 0).all() and (st[0].cpu()[~m][..., 16:20] != 0).any()
+        if t == 20:                            # set_state makes the arrays authoritative until the next step
+            s20, rr, ps, cnt = [x.clone() for x in st]
+            s20[..., 13:20] = torch.rand_like(s20[..., 13:20])
+            lean.set_state(s20, rr, ps, cnt); twin.set_state(s20, rr, ps, cnt)
+            assert torch.equal(same()[0][..., 13:20], s20[..., 13:20])
+    assert nonzero
+    lean.close(); twin.close()
