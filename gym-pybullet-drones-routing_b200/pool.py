@@ -3,7 +3,7 @@
 One ``env.step()`` of 65,536 envs is a single wave of CTAs: while its last blocks compute and store, and across the kernel
 boundary, DRAM idles.  Independent env sets have no such dependency on each other, so a trainer that keeps several pools
 (what ``SubprocVecEnv`` workers are in the single-process reference, ``examples/learn.py:53-57``) can overlap them:
-measured 10.97 -> 8.6 us per 65,536-env step with 8 pools (``python bench.py --streams 8``, profiles/README.md).
+measured 10.7 -> 8.2 us per 65,536-env step with 8 pools (``python bench.py --streams 8``, profiles/README.md).
 
 Each pool's own steps stay ordered (they run on the pool's stream); ``wait(j)`` orders the CALLER's stream behind pool
 ``j``'s latest step before its outputs are read.  Nothing here synchronises the host.
