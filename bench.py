@@ -369,6 +369,7 @@ def b200_arm(a):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_note": (tr or {}).get("note"),
+                "traffic_steady_state": ((tr or {}).get("steady_state_bytes_per_env_step") or 0) * E or None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel<%s,LEAN,N=1,VEC>" % ("double" if a.precision == "f64" else "float"),
                 "kernel_ms_per_launch": per_launch_ms}
