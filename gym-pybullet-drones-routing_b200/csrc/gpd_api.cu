@@ -89,7 +89,7 @@ static const CUtensorMap* get_tmap(gpd_sim* s, const void* base, bool edge = fal
     if (it != cache.end()) return &it->second;
     encode_tiled_fn enc = get_encode_fn();
     if (!enc || ((uintptr_t)base & 15)) return nullptr;
-    if (cache.size() > 64) cache.clear();
+    if (cache.size() > 512) cache.clear();      // trajectory-chained rollouts use one buffer per step (rollout.py)
     CUtensorMap tm;
     cuuint64_t gdim[2] = { (cuuint64_t)s->W, (cuuint64_t)s->D };
     cuuint64_t gstr[1] = { (cuuint64_t)s->W * 4 };

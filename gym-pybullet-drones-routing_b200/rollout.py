@@ -11,6 +11,19 @@ from typing import Callable
 import torch
 
 
+def _rollout_chain(sim, policy, n_steps, obs, actions, rewards, terminated, truncated):
+    """n_steps of (policy -> gpd_step) where the trajectory buffer IS the observation chain: step t reads the action ring
+    from ``obs[t]`` and writes ``obs[t + 1]``, rewards and flags land in their trajectory rows — no per-step copies.  One
+    copy in (the env's current observation) and one out (``adopt_obs``) per rollout keep the env usable eagerly."""
+    obs[0].copy_(sim.obs)
+    for t in range(n_steps):
+        with torch.no_grad():
+            a = policy(obs[t])
+        actions[t].copy_(a.reshape(actions[t].shape))
+        sim.step_into(actions[t], obs[t], obs[t + 1], rewards[t], terminated[t], truncated[t])
+    sim.adopt_obs(obs[n_steps])
+
+
 class GraphedRollout:
     """Collects trajectories ``obs[t], action[t], reward[t], terminated[t], truncated[t]`` for ``t < n_steps``.
 
@@ -54,20 +67,83 @@ class GraphedRollout:
         self.graph = g
 
     def _body(self):
-        sim = self.sim
-        self.obs[0].copy_(sim.obs)
-        for t in range(self.n_steps):
-            with torch.no_grad():
-                a = self.policy(self.obs[t])
-            self.actions[t].copy_(a.reshape(self.actions[t].shape))
-            o, r, te, tr = sim.step(self.actions[t])
-            self.obs[t + 1].copy_(o)
-            self.rewards[t].copy_(r)
-            self.terminated[t].copy_(te)
-            self.truncated[t].copy_(tr)
+        _rollout_chain(self.sim, self.policy, self.n_steps, self.obs, self.actions, self.rewards, self.terminated, self.truncated)
 
     def run(self):
         """One rollout = one graph launch.  Returns views of the trajectory buffers (overwritten by the next run)."""
         self.env._state_cache = None
+        self.graph.replay()
+        return self.obs, self.actions, self.rewards, self.terminated.view(torch.bool), self.truncated.view(torch.bool)
+
+
+class GraphedPoolRollout:
+    """``GraphedRollout`` over several independent env pools: one CUDA graph whose branches (one per pool, each on its own
+    captured stream) run ``n_steps`` of (policy -> env.step).  The branches overlap on the device — one pool's kernel
+    boundary and store tail under another pool's loads (``pool.py``; 8 pools of 65,536 envs: 8.2 instead of 10.7 us per
+    step) — and one ``run()`` is still a single graph launch.
+
+    ``envs``    batched aviaries built with ``auto_reset=True`` (same shape); ``policy`` as in ``GraphedRollout``
+    Trajectory buffers carry a leading pool axis: ``obs (P, n_steps + 1, E, N, W)``, ``actions (P, n_steps, E, N, A)`` ...
+    """
+
+    def __init__(self, envs, policy: Callable[[torch.Tensor], torch.Tensor], n_steps: int, warmup: int = 2):
+        if n_steps < 2 or n_steps % 2:
+            raise ValueError("n_steps must be even and >= 2 (observation ping-pong period)")
+        self.envs, self.policy, self.n_steps = list(envs), policy, n_steps
+        sims = [e._sim for e in self.envs]
+        if not sims or any(not s.auto_reset for s in sims):
+            raise ValueError("GraphedPoolRollout needs envs built with auto_reset=True")
+        s0 = sims[0]
+        if any((s.E, s.N, s.W, s.A) != (s0.E, s0.N, s0.W, s0.A) for s in sims):
+            raise ValueError("all pools must have the same shape")
+        dev, P = s0.device, len(sims)
+        self.sims = sims
+        self.obs = torch.zeros((P, n_steps + 1, s0.E, s0.N, s0.W), dtype=s0.obs_dtype, device=dev)
+        self.actions = torch.zeros((P, n_steps, s0.E, s0.N, s0.A), dtype=s0.act_dtype, device=dev)
+        self.rewards = torch.zeros((P, n_steps, s0.E), dtype=s0.real, device=dev)
+        self.terminated = torch.zeros((P, n_steps, s0.E), dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros((P, n_steps, s0.E), dtype=torch.uint8, device=dev)
+        self.branches = [torch.cuda.Stream(device=dev) for _ in range(P - 1)]
+        for s in sims:
+            if not s._have_prev:
+                s.reset()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        phases = [s._cur for s in sims]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                self._body()
+        torch.cuda.synchronize(dev)
+        assert phases == [s._cur for s in sims]
+        self.graph = g
+
+    def _branch(self, j):
+        _rollout_chain(self.sims[j], self.policy, self.n_steps, self.obs[j], self.actions[j], self.rewards[j],
+                       self.terminated[j], self.truncated[j])
+
+    def _body(self):
+        main = torch.cuda.current_stream(self.sims[0].device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in self.branches:
+            st.wait_event(fork)
+        for j in range(len(self.sims)):
+            with torch.cuda.stream(main if j == 0 else self.branches[j - 1]):
+                self._branch(j)
+        for st in self.branches:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
+    def run(self):
+        """One rollout of every pool = one graph launch.  Returns views of the trajectory buffers."""
+        for e in self.envs:
+            e._state_cache = None
         self.graph.replay()
         return self.obs, self.actions, self.rewards, self.terminated.view(torch.bool), self.truncated.view(torch.bool)

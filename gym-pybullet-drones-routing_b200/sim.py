@@ -131,6 +131,30 @@ class BatchedSim:
         self._cur, self._have_prev = nxt, True
         return self.obs_buf[nxt], self.reward, self.terminated, self.truncated
 
+    def step_into(self, actions: torch.Tensor, obs_prev: torch.Tensor, obs_out: torch.Tensor, reward: torch.Tensor,
+                  terminated: torch.Tensor, truncated: torch.Tensor):
+        """``gpd_step`` on caller-owned buffers (the C ABI's ownership model): reads the action ring from
+        ``obs_prev``, writes the new observation to ``obs_out`` and the per-env outputs in place.  A trajectory buffer
+        ``obs[t] -> obs[t + 1]`` can thus be the observation chain itself (no per-step copies; ``rollout.py``).  The
+        internal ping-pong buffers are not touched: call ``adopt_obs`` before going back to ``step``."""
+        for t, dt in ((actions, self.act_dtype), (obs_prev, self.obs_dtype), (obs_out, self.obs_dtype), (reward, self.real),
+                      (terminated, torch.uint8), (truncated, torch.uint8)):
+            if t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("step_into needs contiguous CUDA tensors of the sim's dtypes")
+        if obs_prev.numel() != self.E * self.N * self.W or obs_out.numel() != obs_prev.numel():
+            raise ValueError("observation buffers must hold E x N x W elements")
+        if reward.numel() != self.E or terminated.numel() != self.E or truncated.numel() != self.E:
+            raise ValueError("reward / terminated / truncated must hold E elements")
+        if actions.numel() != self.E * self.N * self.A:
+            raise ValueError(f"actions must have {self.E}x{self.N}x{self.A} elements, got {tuple(actions.shape)}")
+        _lib.check(self.lib.gpd_step(self.h, _ptr(actions), _ptr(obs_prev), _ptr(obs_out), _ptr(reward), _ptr(terminated),
+                                     _ptr(truncated), self._p_out[3], self._stream()))
+
+    def adopt_obs(self, obs: torch.Tensor):
+        """Makes ``obs`` (the latest observation written by ``step_into``) the current internal observation."""
+        self.obs_buf[self._cur].copy_(obs.reshape(self.obs_buf[self._cur].shape))
+        self._have_prev = True
+
     # host-buffer path: what a numpy call site (the reference's own step signature) sees
     def step_host(self, actions: np.ndarray, out=None):
         adt = self.np_real if self.is_ctrl else np.float32

@@ -986,3 +986,33 @@ def test_cuda_f32_lean_state_export_matches_explicit_aux_arrays(act, N, monkeypa
             assert torch.equal(same()[0][..., 13:20], s20[..., 13:20])
     assert nonzero
     lean.close(); twin.close()
+
+
+def test_cuda_graphed_pool_rollout_matches_single_pool_rollouts():
+    """GraphedPoolRollout (one graph, one branch per pool) == independent GraphedRollouts of the same pools, bit-exact."""
+    from gpd_b200.envs import HoverAviary
+    from gpd_b200.rollout import GraphedPoolRollout, GraphedRollout
+    torch.manual_seed(1)
+    E, T, P = 300, 4, 3
+    W1 = (0.05 * torch.randn(72, 16)).cuda()
+    W2 = (0.5 * torch.randn(16, 4)).cuda()
+
+    def policy(obs):
+        return torch.tanh(torch.tanh(obs.reshape(obs.shape[0], -1) @ W1) @ W2).reshape(obs.shape[0], 1, 4)
+
+    rng = np.random.default_rng(2)
+    inits = [_random_init(rng, E, 1) for _ in range(P)]
+    mk = lambda j: HoverAviary(num_envs=E, auto_reset=True, precision="f32", initial_xyzs=inits[j][0], initial_rpys=inits[j][1])
+    pool = GraphedPoolRollout([mk(j) for j in range(P)], policy, T)
+    singles = [GraphedRollout(mk(j), policy, T) for j in range(P)]
+    for rep in range(2):
+        obs, act, rew, term, trunc = pool.run()
+        torch.cuda.synchronize()
+        for j in range(P):
+            o1, a1, r1, te1, tr1 = singles[j].run()
+            torch.cuda.synchronize()
+            assert torch.equal(obs[j], o1) and torch.equal(act[j], a1) and torch.equal(rew[j], r1)
+            assert torch.equal(term[j], te1) and torch.equal(trunc[j], tr1)
+    assert not torch.equal(obs[0], obs[1])          # the pools really are different simulations
+    with pytest.raises(ValueError):
+        GraphedPoolRollout([], policy, T)
