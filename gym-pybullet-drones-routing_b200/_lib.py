@@ -26,7 +26,7 @@ MODEL_CODES = {"cf2x": 0, "cf2p": 1, "racer": 2}
 SYMBOLS = [
     "gpd_version", "gpd_last_error", "gpd_device_count", "gpd_create", "gpd_destroy", "gpd_obs_width",
     "gpd_action_width", "gpd_substeps", "gpd_set_init_poses", "gpd_reset", "gpd_step", "gpd_step_host",
-    "gpd_reset_host", "gpd_get_state", "gpd_set_state", "gpd_pid_compute", "gpd_force_ground_effect",
+    "gpd_reset_host", "gpd_get_state", "gpd_note_latest_obs", "gpd_set_state", "gpd_pid_compute", "gpd_force_ground_effect",
     "gpd_force_drag", "gpd_force_downwash", "gpd_rollout_pid", "gpd_episode_stats", "gpd_grid_size",
     "gpd_set_timeline_buffer", "gpd_count_nonfinite",
 ]
@@ -142,6 +142,7 @@ def load(path: str | None = None):
     L.gpd_step_host.argtypes = [vp, vp, vp, vp, u8p, u8p, vp, vp]
     L.gpd_reset_host.argtypes = [vp, u8p, vp, vp]
     L.gpd_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.gpd_note_latest_obs.argtypes = [vp, vp]
     L.gpd_set_state.argtypes = [vp, vp, vp, vp, vp, vp]
     L.gpd_pid_compute.argtypes = [C.c_int, C.c_int, C.POINTER(PidParamsC), i64, dbl,
                                   vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -620,6 +620,13 @@ int gpd_get_state(gpd_sim* s, void* state20, void* rpy_rates, void* pid_state, i
     return GPD_OK;
 }
 
+int gpd_note_latest_obs(gpd_sim* s, const void* obs)
+{
+    if (!s || !obs) return fail(GPD_ERR_INVALID, "gpd_note_latest_obs: null argument");
+    s->last_obs = obs;
+    return GPD_OK;
+}
+
 int gpd_set_state(gpd_sim* s, const void* state20, const void* rpy_rates, const void* pid_state,
                   const int32_t* step_counter, void* stream)
 {

@@ -154,6 +154,7 @@ class BatchedSim:
         """Makes ``obs`` (the latest observation written by ``step_into``) the current internal observation."""
         self.obs_buf[self._cur].copy_(obs.reshape(self.obs_buf[self._cur].shape))
         self._have_prev = True
+        _lib.check(self.lib.gpd_note_latest_obs(self.h, self._p_obs[self._cur]))     # `obs` may be released by its owner
 
     # host-buffer path: what a numpy call site (the reference's own step signature) sees
     def step_host(self, actions: np.ndarray, out=None):

@@ -167,6 +167,9 @@ int gpd_reset_host(gpd_sim* sim, const uint8_t* env_mask, void* obs_out, void* s
  * row: gpd_get_state (and a masked gpd_reset) re-derive them, bit-exactly, from the observation buffer most recently
  * passed as obs_out - the same buffer the next gpd_step needs intact as obs_prev. */
 int gpd_get_state(gpd_sim* sim, void* state20, void* rpy_rates, void* pid_state, int32_t* step_counter, void* stream);
+/* Tells the library which device buffer now holds the latest observation (a caller that copied it elsewhere and is about to
+ * release the buffer it passed as obs_out). Only FP32 KIN sims with an RPM-type action and no force model read it back. */
+int gpd_note_latest_obs(gpd_sim* sim, const void* obs);
 int gpd_set_state(gpd_sim* sim, const void* state20, const void* rpy_rates, const void* pid_state,
                   const int32_t* step_counter, void* stream);
 

@@ -542,6 +542,15 @@ def test_cuda_graphed_rollout_matches_eager_stepping():
             assert torch.equal(act[t], a) and torch.equal(rew[t], r2)
             assert torch.equal(term[t], te2.view(torch.bool)) and torch.equal(trunc[t], tr2.view(torch.bool))
         assert torch.equal(obs[T], env_e._sim.obs)
+        # exported state (ang_v / last_clipped_action are re-derived from the latest observation in this lean FP32 sim)
+        assert all(torch.equal(x, y) for x, y in zip(env_g._sim.get_state(), env_e._sim.get_state()))
+    del ro, obs, act, rew, term, trunc          # the trajectory buffers go away: the env must not depend on them
+    torch.cuda.empty_cache()
+    junk = torch.full((E * 73 * 8,), 7.0, device="cuda")
+    assert all(torch.equal(x, y) for x, y in zip(env_g._sim.get_state(), env_e._sim.get_state()))
+    a = policy(env_e._sim.obs)
+    assert all(torch.equal(x, y) for x, y in zip(env_g._sim.step(a), env_e._sim.step(a)))
+    del junk
     with pytest.raises(ValueError):
         GraphedRollout(env_g, policy, 3)
     env_g.close(); env_e.close()
