@@ -380,13 +380,14 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     };
     // defaults (measured, profiles/README.md): 64 physics threads for the lean FP32 single-drone kernel (64 registers: more,
     // smaller CTAs balance better over 148 SMs) and for A < 4, 128 for the other single-drone kernels; multi-drone envs
-    // 224 (+ the DMA warp = 256), 128 with downwash
+    // 224 (+ the DMA warp = 256), 64 with downwash
     const bool f64 = cfg->precision == GPD_F64;
     const bool rpm_like = cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_ONE_D_RPM || cfg->action_type == GPD_ACT_CTRL_RPM;
     const bool lean = rpm_like && cfg->physics_flags == 0;
     int P0 = 64;
     if (N == 1) P0 = (A == 4 && (f64 || !lean)) ? 128 : 64;      // A < 4: the 32 funnel-copy lanes limit the tile to 64 rows
-    else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 128 : 224;    // downwash: a block barrier per substep favours smaller CTAs
+    else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 64 : 224;     // downwash: two block barriers per substep favour small CTAs
+                                                                // (512 envs x 64 drones: 17.4 us at 64 threads, 24.1 at 128)
     Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0);
     if (!cfg->threads_per_block) {
         // Wave quantisation: a launch of 1..4 waves pays for its partly filled last wave (MultiHover x2 FP32 at 32,768
