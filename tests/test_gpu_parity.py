@@ -1025,3 +1025,98 @@ def test_cuda_graphed_pool_rollout_matches_single_pool_rollouts():
     assert not torch.equal(obs[0], obs[1])          # the pools really are different simulations
     with pytest.raises(ValueError):
         GraphedPoolRollout([], policy, T)
+
+
+def _fuzz_config(seed):
+    rng = np.random.default_rng(1000 + seed)
+    env_kind = rng.choice(["hover", "multihover", "ctrl"])
+    N = 1 if env_kind == "hover" else int(rng.choice([1, 2, 3, 5, 9, 33]))
+    if env_kind == "multihover" and N == 1:
+        N = 2
+    freq = [(240, 30), (240, 48), (240, 240), (120, 30), (96, 48), (60, 20)][rng.integers(6)]
+    model = [DroneModel.CF2X, DroneModel.CF2P, DroneModel.RACE][rng.integers(3)]
+    if env_kind == "ctrl":
+        act = rng.choice(["ctrl_rpm", "ctrl_vel"])
+    else:
+        act = rng.choice(["rpm", "one_d_rpm", "pid", "vel", "one_d_pid"])
+    if act in ("pid", "vel", "one_d_pid", "ctrl_vel") and model == DroneModel.RACE:
+        model = DroneModel.CF2X                                   # no controller for the racer (BaseRLAviary.py:77-78)
+    flags = int(rng.integers(8)) if N > 1 else int(rng.integers(4))   # downwash needs neighbours
+    E = int(rng.choice([1, 7, 63, 64, 65, 130, 257]))
+    return rng, dict(model=model, env_kind=env_kind, action_type=act, num_drones=N, pyb_freq=freq[0], ctrl_freq=freq[1],
+                     physics_flags=flags), E, int(rng.choice([0, 32, 64, 96, 160, 256]))
+
+
+import os as _os
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("GPD_FUZZ_SEEDS", "24"))))     # GPD_FUZZ_SEEDS=400 for a campaign
+def test_cuda_f64_fuzz_vs_oracle(seed):
+    """Differential fuzzing: random (model, env, N, frequencies, action type, force models, ragged E, block size) against
+    the oracle, FP64, 12 ctrl steps from random poses; everything the step returns plus the exported state."""
+    rng, kw, E, tpb = _fuzz_config(seed)
+    N = kw["num_drones"]
+    A = {"rpm": 4, "one_d_rpm": 1, "pid": 3, "vel": 4, "one_d_pid": 1, "ctrl_rpm": 4, "ctrl_vel": 4}[kw["action_type"]]
+    xyz = np.stack([rng.uniform(-1, 1, (E, N)), rng.uniform(-1, 1, (E, N)), rng.uniform(0.05, 1.5, (E, N))], -1)
+    if kw["physics_flags"] & 4:                                   # keep clear of the downwash singularities (DESIGN 3.4)
+        xyz[..., 2] = 0.2 + 0.11 * np.argsort(rng.random((E, N)), axis=1)
+    kw.update(init_xyz=xyz, init_rpy=rng.uniform(-.2, .2, (E, N, 3)))
+    hover = load_drone_params(kw["model"]).HOVER_RPM
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E, tpb=tpb)
+    obs0 = sim.reset()
+    assert np.max(np.abs(obs0.double().cpu().numpy() - ref.obs)) <= 1e-6, kw
+    for t in range(12):
+        if kw["action_type"] == "ctrl_rpm":
+            a = hover * (1 + 0.05 * rng.uniform(-1, 1, (E, N, A)))
+            at = torch.from_numpy(a).cuda()
+        elif kw["action_type"] == "ctrl_vel":
+            a = rng.uniform(-1, 1, (E, N, A))
+            at = torch.from_numpy(a).cuda()
+        else:
+            a = (0.3 * rng.standard_normal((E, N, A))).astype(np.float32)
+            at = torch.from_numpy(a).cuda()
+        obs, rew, term, trunc = sim.step(at)
+        o_ref, r_ref, te_ref, tr_ref = ref.step(a)
+        st, _, cnt = state_np(sim)
+        rs = np.concatenate([ref.state20, ref.rpy_rates], axis=-1)
+        tol = 1e-6 if kw["action_type"] in ("vel", "ctrl_vel") else 1e-9      # float32 BLAS sdot in the reference's VEL map
+        for sl, nm in ((S_POS, "pos"), (S_VEL, "vel"), (S_RATES, "rates"), (S_ANGV, "ang_v"), (S_RPM, "rpm")):
+            assert rel_err(st[..., sl], rs[..., sl]) <= tol, (kw, E, tpb, t, nm)
+        assert quat_err(st[..., S_QUAT], rs[..., S_QUAT]) <= tol, (kw, t)
+        assert np.array_equal(cnt, ref.step_counter)
+        assert np.max(np.abs(obs.double().cpu().numpy() - o_ref) / np.maximum(np.abs(o_ref), 1.0)) <= 1e-6, (kw, t)
+        assert np.max(np.abs(rew.double().cpu().numpy() - r_ref) / np.maximum(np.abs(r_ref), 1e-3)) <= 10 * tol
+        assert np.array_equal(term.cpu().numpy(), te_ref) and np.array_equal(trunc.cpu().numpy(), tr_ref), (kw, t)
+    sim.close()
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("GPD_FUZZ_SEEDS", "16"))))
+def test_cuda_f32_fuzz_vs_oracle(seed):
+    """FP32 throughput mode under the same random configurations (RPM-type actions, no downwash: the well-conditioned
+    paths), 8 ctrl steps: position / velocity within 1e-4 of the FP64 oracle, the exported rpm exact to FP32 rounding."""
+    rng, kw, E, tpb = _fuzz_config(seed)
+    kw["action_type"] = "ctrl_rpm" if kw["env_kind"] == "ctrl" else ("rpm" if seed % 3 else "one_d_rpm")
+    kw["physics_flags"] &= 3
+    N = kw["num_drones"]
+    A = 1 if kw["action_type"] == "one_d_rpm" else 4
+    xyz = np.stack([rng.uniform(-1, 1, (E, N)), rng.uniform(-1, 1, (E, N)), rng.uniform(0.05, 1.5, (E, N))], -1)
+    kw.update(init_xyz=xyz, init_rpy=rng.uniform(-.2, .2, (E, N, 3)))
+    hover = load_drone_params(kw["model"]).HOVER_RPM
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E, precision="f32", tpb=tpb)
+    sim.reset()
+    for t in range(8):
+        if kw["action_type"] == "ctrl_rpm":
+            a32 = (hover * (1 + 0.05 * rng.uniform(-1, 1, (E, N, A)))).astype(np.float32)
+            a = a32.astype(np.float64)                             # the oracle sees exactly the float32 command
+        else:
+            a32 = a = (0.3 * rng.standard_normal((E, N, A))).astype(np.float32)
+        sim.step(torch.from_numpy(a32).cuda())
+        ref.step(a)
+        st, _, cnt = state_np(sim)
+        rs = np.concatenate([ref.state20, ref.rpy_rates], axis=-1)
+        assert rel_err(st[..., S_POS], rs[..., S_POS]) <= 1e-4 and rel_err(st[..., S_VEL], rs[..., S_VEL]) <= 1e-4, (kw, E, tpb, t)
+        assert rel_err(st[..., S_RPM], rs[..., S_RPM]) <= 1e-6 and rel_err(st[..., S_ANGV], rs[..., S_ANGV]) <= 2e-3, (kw, t)
+        assert np.array_equal(cnt, ref.step_counter)
+    sim.close()
