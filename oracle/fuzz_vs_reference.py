@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE.  Differential fuzzing of the C oracle against the UNMODIFIED reference Python (run under the
 stand-ins of oracle/refshim, like oracle/gen_golden.py): random (env class, drone model, drones, ctrl frequency, action
-type, initial poses), open-loop action replay, every ctrl step compared.  Needs the reference tree (this container only):
+type, initial poses, DYN-form force models), open-loop action replay, every ctrl step compared.  Needs the reference tree (this container only):
 
     python oracle/fuzz_vs_reference.py --ref /root/reference --seeds 40        # prints one JSON line
 """
@@ -46,6 +46,13 @@ def one_case(R, seed):
     xyz = rng.uniform([-1, -1, 0.1], [1, 1, 1.5], size=(n, 3))
     rpy = rng.uniform(-0.3, 0.3, size=(n, 3))
     dm = DM(model)
+    # every third case: the DYN-form composite (the reference's own _groundEffect/_drag/_downwash values injected)
+    flags = 0
+    if seed % 3 == 0:
+        flags = int(rng.integers(1, 8)) if n > 1 else int(rng.integers(1, 4))
+        xyz[:, 2] = 0.05 + 0.13 * rng.permutation(n) + rng.uniform(0, 0.02, n)       # near the ground, distinct heights
+    C = {k: (G.make_composite_class(R, k, flags) if flags else R[k]) for k in ("CtrlAviary", "HoverAviary", "MultiHoverAviary")}
+    R = dict(R, **C)
     with G.quiet():
         if kind == "ctrl":
             env = R["CtrlAviary"](drone_model=dm, num_drones=n, initial_xyzs=xyz, initial_rpys=rpy, physics=P.DYN, pyb_freq=240,
@@ -59,7 +66,7 @@ def one_case(R, seed):
     dp = load_drone_params(DMh(model))
     target = None if kind == "ctrl" else np.asarray(env.TARGET_POS, np.float64).reshape(-1, 3)
     pid = default_pid_params(DMh.CF2X) if closed_loop else None          # in-env controllers are CF2X (BaseRLAviary.py:75)
-    sim = orc.OracleSim(dp, 1, num_drones=n, env_kind=kind, action_type=act, pyb_freq=240, ctrl_freq=freq, physics_flags=0,
+    sim = orc.OracleSim(dp, 1, num_drones=n, env_kind=kind, action_type=act, pyb_freq=240, ctrl_freq=freq, physics_flags=flags,
                         pid_params=pid, init_xyz=xyz[None], init_rpy=rpy[None], target_pos=target)
     na, a = (n, 4) if kind == "ctrl" else env.action_space.shape
     if kind == "ctrl":
@@ -83,7 +90,7 @@ def one_case(R, seed):
         worst = max(worst, float(q.max()), abs(float(r) - float(r2[0])) / max(abs(float(r)), 1e-3))
         worst = max(worst, float(np.max(np.abs(np.asarray(o, np.float64) - o2[0]) / np.maximum(np.abs(o2[0]), 1.0))) * 1e-3)
         flags_ok &= bool(te) == bool(te2[0]) and bool(tr) == bool(tr2[0]) and int(env.step_counter) == int(sim.step_counter[0])
-    return dict(seed=seed, kind=kind, model=model, n=n, freq=freq, act=act, steps=steps, worst=worst, flags_ok=flags_ok)
+    return dict(seed=seed, kind=kind, model=model, n=n, freq=freq, act=act, flags=flags, steps=steps, worst=worst, flags_ok=flags_ok)
 
 
 def main():
