@@ -10,7 +10,8 @@
  * (reference tests/test_examples.py:1-15 never run Physics.DYN).  The oracle is
  * pinned instead against outputs of the reference's own unmodified Python run in
  * the build container under the stand-ins in oracle/refshim (generator:
- * oracle/gen_golden.py, fixtures: tests/golden/).  Bullet's three closed-form
+ * oracle/gen_golden.py, fixtures: tests/golden/) and, live, by oracle/fuzz_vs_reference.py
+ * (random configurations replayed in the reference and here).  Bullet's three closed-form
  * converters are restated from Bullet's published formulas and could not be
  * checked against a real pybullet wheel ("parity unpinned" w.r.t. Bullet itself).
  *
