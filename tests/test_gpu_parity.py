@@ -1120,3 +1120,46 @@ def test_cuda_f32_fuzz_vs_oracle(seed):
         assert rel_err(st[..., S_RPM], rs[..., S_RPM]) <= 1e-6 and rel_err(st[..., S_ANGV], rs[..., S_ANGV]) <= 2e-3, (kw, t)
         assert np.array_equal(cnt, ref.step_counter)
     sim.close()
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("GPD_FUZZ_SEEDS", "12"))))
+def test_cuda_f64_fuzz_auto_reset_vs_oracle(seed):
+    """The bench path's in-kernel auto-reset under random RL configurations: the oracle is reset by hand wherever it reports
+    an episode end; observations, flags, exported state and Monitor-style statistics must keep agreeing for 40 steps."""
+    rng, kw, E, tpb = _fuzz_config(seed + 5000)
+    if kw["env_kind"] == "ctrl":
+        kw["env_kind"], kw["num_drones"] = "hover", 1
+    kw["action_type"] = ["rpm", "one_d_rpm", "pid", "one_d_pid"][seed % 4]
+    if kw["action_type"] in ("pid", "one_d_pid") and kw["model"] == DroneModel.RACE:
+        kw["model"] = DroneModel.CF2P
+    N = kw["num_drones"]
+    kw["physics_flags"] &= 3
+    A = {"rpm": 4, "one_d_rpm": 1, "pid": 3, "one_d_pid": 1}[kw["action_type"]]
+    xyz = np.stack([rng.uniform(-1, 1, (E, N)), rng.uniform(-1, 1, (E, N)), rng.uniform(0.05, 1.5, (E, N))], -1)
+    kw.update(init_xyz=xyz, init_rpy=rng.uniform(-.2, .2, (E, N, 3)))
+    ref = make_oracle(kw, num_envs=E)
+    sim = make_sim(kw, num_envs=E, auto_reset=True, tpb=tpb)
+    sim.reset()
+    n_ep, sum_len, ep_len = 0, 0, np.zeros(E, int)
+    for t in range(40):
+        a = rng.uniform(-1, 1, (E, N, A)).astype(np.float32)
+        obs, rew, term, trunc = sim.step(torch.from_numpy(a).cuda())
+        o_ref, r_ref, te_ref, tr_ref = ref.step(a)
+        o_ref = o_ref.copy()
+        assert np.array_equal(term.cpu().numpy(), te_ref) and np.array_equal(trunc.cpu().numpy(), tr_ref), (kw, E, t)
+        assert np.max(np.abs(rew.cpu().numpy() - r_ref) / np.maximum(np.abs(r_ref), 1e-3)) <= 1e-8
+        done = (te_ref | tr_ref).astype(bool)
+        ep_len += 1
+        n_ep += int(done.sum()); sum_len += int(ep_len[done].sum()); ep_len[done] = 0
+        if done.any():
+            o_ref[done] = ref.reset(done.astype(np.uint8))[done]
+        assert np.max(np.abs(obs.double().cpu().numpy() - o_ref) / np.maximum(np.abs(o_ref), 1.0)) <= 1e-6, (kw, E, t)
+        st, _, cnt = state_np(sim)
+        rs = np.concatenate([ref.state20, ref.rpy_rates], axis=-1)
+        tol = 1e-6 if kw["action_type"] in ("pid", "one_d_pid") else 1e-9     # closed loops amplify libm-level differences
+        for sl in (S_POS, S_VEL, S_RATES, S_ANGV, S_RPM):
+            assert rel_err(st[..., sl], rs[..., sl]) <= tol, (kw, E, t, sl)
+        assert np.array_equal(cnt, ref.step_counter)
+    stats = sim.episode_stats()
+    assert stats[0] == n_ep and stats[2] == sum_len and stats[6] == 40 * E
+    sim.close()
