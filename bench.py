@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-async-extra", action="store_true", help="skip the informational multi-stream measurement")
     return ap.parse_args()
 
 
@@ -228,7 +229,7 @@ def b200_arm(a):
     nstreams = max(1, min(a.streams, nsets))
     pool = [torch.cuda.Stream(device=dev) for _ in range(nstreams - 1)]
 
-    def run_steps(n):
+    def run_steps(n, nstreams=nstreams, pool=pool):
         if nstreams == 1:
             for k in range(n):
                 envs[k % nsets]._sim.step(acts[k])
@@ -321,6 +322,37 @@ def b200_arm(a):
         ms = float(t.item())
     value = world * E * 1 * S * K / (ms * 1e-3)
 
+    # ---- informational: the same K-step job with the env sets as async pools on their own streams (never the headline) ----
+    async_info = None
+    if nstreams == 1 and graph is not None and nsets >= 2 and not a.no_async_extra:
+        try:
+            ns2 = min(8, nsets)
+            pool2 = [torch.cuda.Stream(device=dev) for _ in range(ns2 - 1)]
+            side = torch.cuda.Stream()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g2, stream=side):
+                    run_steps(period, ns2, pool2)
+            torch.cuda.synchronize()
+            reps2 = max(1, min(reps, 250))
+            for _ in range(20):
+                g2.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps2):
+                g2.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / (reps2 * period)
+            async_info = {"streams": ns2, "ms_per_step": ms2, "steps": reps2 * period,
+                          "value_this_rank": E * S / (ms2 * 1e-3),
+                          "note": "env set j steps on stream j % streams (its own steps stay ordered, independent sets overlap): "
+                                  "what a trainer with several env pools gets (pool.py); informational, not the headline"}
+        except Exception as ex:
+            async_info = {"error": repr(ex)[:200]}
+            torch.cuda.synchronize()
+
     # ---- episode statistics: the only collective (NCCL all-reduce of 6 sums + min/max), outside the step path ----
     stats = np.zeros(8)
     for e in envs:
@@ -376,6 +408,8 @@ def b200_arm(a):
         if nstreams > 1:
             roof["note"] = (f"{nstreams} streams: launches of independent env sets overlap, so kernel_ms_per_launch is the "
                             "throughput-equivalent time per launch, not one launch's duration")
+        if async_info and "ms_per_step" in async_info and algo:
+            async_info["frac_of_hbm_peak"] = algo * E / (async_info["ms_per_step"] * 1e-3) / 1e9 / peak
         cpu = None
         if not a.no_cpu:
             r = cpu_run(a, seconds=a.cpu_seconds)
@@ -396,6 +430,7 @@ def b200_arm(a):
                     "steps": a.e2e_steps, "api": "HoverAviary.step(numpy) -> gpd_step_host (pinned host buffers)"},
             "gpu_launches": K,
             "roofline": roof,
+            "async_pools": async_info,
             "cpu_baseline": cpu,
             "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1),
                               "mean_length": stats[2] / max(stats[0], 1), "env_steps": stats[6]},

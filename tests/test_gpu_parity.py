@@ -914,6 +914,10 @@ def test_cuda_bench_contract_line(extra):
     assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 16 and d["e2e"]["d2h_bytes_per_step"] == 4096 * (72 * 4 + 6)
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["config"]["streams"] == (2 if "--streams" in extra else 1)
+    if not extra or "--steps" in extra:                             # informational multi-stream figure beside the headline
+        assert d["async_pools"]["streams"] == 2 and d["async_pools"]["ms_per_step"] > 0
+    else:
+        assert d["async_pools"] is None
 
 
 def test_cuda_async_env_pools_match_sequential_stepping():
