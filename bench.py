@@ -353,6 +353,34 @@ def b200_arm(a):
             async_info = {"error": repr(ex)[:200]}
             torch.cuda.synchronize()
 
+    # ---- informational: one env set alone (46 MB working set: L2-resident; SURVEY 8d asks for flushed AND unflushed) ----
+    l2_info = None
+    if graph is not None and not a.no_async_extra:
+        try:
+            side = torch.cuda.Stream()
+            g3 = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g3, stream=side):
+                    for k in range(period):
+                        envs[0]._sim.step(acts[k % 2])
+            torch.cuda.synchronize()
+            reps3 = max(1, min(reps, 250))
+            for _ in range(20):
+                g3.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps3):
+                g3.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            l2_info = {"ms_per_step": e0.elapsed_time(e1) / (reps3 * period), "steps": reps3 * period,
+                       "note": "ONE env set stepped back to back (working set < 126 MB L2, no rotation): what a single-set "
+                               "rollout sees; not an HBM number, informational"}
+        except Exception as ex:
+            l2_info = {"error": repr(ex)[:200]}
+            torch.cuda.synchronize()
+
     # ---- episode statistics: the only collective (NCCL all-reduce of 6 sums + min/max), outside the step path ----
     stats = np.zeros(8)
     for e in envs:
@@ -431,6 +459,7 @@ def b200_arm(a):
             "gpu_launches": K,
             "roofline": roof,
             "async_pools": async_info,
+            "l2_resident": l2_info,
             "cpu_baseline": cpu,
             "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1),
                               "mean_length": stats[2] / max(stats[0], 1), "env_steps": stats[6]},
