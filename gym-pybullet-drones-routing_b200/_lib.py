@@ -28,7 +28,9 @@ SYMBOLS = [
     "gpd_action_width", "gpd_substeps", "gpd_set_init_poses", "gpd_reset", "gpd_step", "gpd_step_host",
     "gpd_reset_host", "gpd_get_state", "gpd_note_latest_obs", "gpd_set_state", "gpd_pid_compute", "gpd_force_ground_effect",
     "gpd_force_drag", "gpd_force_downwash", "gpd_rollout_pid", "gpd_episode_stats", "gpd_grid_size",
-    "gpd_set_timeline_buffer", "gpd_count_nonfinite",
+    "gpd_set_timeline_buffer", "gpd_count_nonfinite", "gpd_set_targets", "gpd_mirror_alloc", "gpd_mirror_free",
+    "gpd_mirror_attach", "gpd_mirror_row", "gpd_step_mirror", "gpd_step_mirror_begin", "gpd_step_mirror_end",
+    "gpd_reset_mirror", "gpd_nccl_unique_id", "gpd_nccl_comm_init", "gpd_nccl_comm_destroy", "gpd_adjacency",
 ]
 
 
@@ -150,7 +152,21 @@ def load(path: str | None = None):
     L.gpd_force_drag.argtypes = [C.c_int, C.c_int, C.POINTER(DroneParamsC), i64, vp, vp, vp, vp, vp]
     L.gpd_force_downwash.argtypes = [C.c_int, C.c_int, C.POINTER(DroneParamsC), i64, i32, vp, vp, vp]
     L.gpd_rollout_pid.argtypes = [vp, i32, vp, i32, vp, vp, vp]
-    L.gpd_episode_stats.argtypes = [vp, C.POINTER(dbl), C.c_int, vp]
+    L.gpd_episode_stats.argtypes = [vp, C.POINTER(dbl), C.c_int, vp, vp]
+    L.gpd_set_targets.argtypes = [vp, C.POINTER(dbl), C.c_int]
+    L.gpd_mirror_alloc.argtypes = [i64, i64, C.POINTER(vp)]
+    L.gpd_mirror_free.argtypes = [vp]
+    L.gpd_mirror_attach.argtypes = [vp, vp, i64, i64, i64]
+    L.gpd_mirror_row.argtypes = [vp]
+    L.gpd_mirror_row.restype = i64
+    L.gpd_step_mirror.argtypes = [vp, vp, vp, vp, vp, u8p, u8p, vp, C.POINTER(i64), vp]
+    L.gpd_step_mirror_begin.argtypes = [vp, vp, vp, vp, vp, u8p, u8p, vp, vp]
+    L.gpd_step_mirror_end.argtypes = [vp, C.POINTER(i64), vp]
+    L.gpd_reset_mirror.argtypes = [vp, u8p, vp, vp, C.POINTER(i64), vp]
+    L.gpd_nccl_unique_id.argtypes = [C.c_char_p]
+    L.gpd_nccl_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.gpd_nccl_comm_destroy.argtypes = [vp]
+    L.gpd_adjacency.argtypes = [vp, dbl, vp, vp]
     L.gpd_grid_size.argtypes = [vp]
     L.gpd_count_nonfinite.argtypes = [vp, C.POINTER(C.c_longlong), vp]
     L.gpd_set_timeline_buffer.argtypes = [vp, vp]

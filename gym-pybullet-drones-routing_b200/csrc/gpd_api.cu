@@ -10,10 +10,16 @@
 #include <unordered_map>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>          // types only: the library is bound at run time (dlopen), never linked
+#include <xmmintrin.h>
+
 #include "gpd_internal.h"
 
 namespace gpd {
 cudaError_t launch_stats(const StatSlot* slots, int64_t nslots, double* out8, int clear, StatSlot* slots_mut, cudaStream_t st);
+cudaError_t launch_stats_combine(const double* gathered, int nranks, double* out8, cudaStream_t st);
+cudaError_t launch_transpose_cols(const float* obs, int64_t D, int W, int j0, int j1, float* out, int64_t ld, cudaStream_t st);
 }
 
 using namespace gpd;
@@ -56,6 +62,26 @@ static int fail(int code, const char* fmt, ...)
                         "%s failed: %s", #call, cudaGetErrorString(_e));                           \
     } while (0)
 
+// Host mirror of the RL observation (gpd_step_mirror): the observation window of every drone lives in a feature-major log in
+// pinned host memory, log[row][col]: row = observation feature, col = drone.  The window of step t is rows [row, row + W):
+// 12 kin rows then the A*B ring rows, oldest -> newest.  A step slides the window by A rows: the device sends only what it
+// computed (12 kin rows, reward, flags); the newest action is written by the host from its own copy; nothing is echoed.
+struct Mirror {
+    float* log = nullptr;
+    int64_t rows = 0, ld = 0, col0 = 0;
+    int64_t row = 0;                // first row of the current window
+    bool valid = false;             // the window matches the device observation `synced_obs` as of sequence `synced_seq`
+    uint64_t synced_seq = 0;
+    const void* synced_obs = nullptr;
+    float* d_kin_t = nullptr;       // device [12][D]
+    float* d_full_t = nullptr;      // device [W][D], refresh scratch (lazy)
+    bool pending = false;           // a begin without its end
+    const void* pending_obs = nullptr;
+    const float* pending_actions = nullptr;
+};
+
+struct TmapEntry { CUtensorMap tm; uint64_t tick; };
+
 struct gpd_sim {
     gpd_config cfg;
     int A, B, W, S;
@@ -64,32 +90,48 @@ struct gpd_sim {
     int dpb = 0;
     int copy_threads = 0;
     const void* last_obs = nullptr;   // the observation buffer most recently written by gpd_step / gpd_reset (device)
+    uint64_t obs_seq = 0;             // bumped whenever the device observation chain advances (or is replaced by the caller)
     std::vector<void*> allocs;
     StepArgs<float> a32;
     StepArgs<double> a64;
     std::vector<double> target_host;
-    // host-buffer path (gpd_step_host): device I/O buffers + obs ping-pong, allocated lazily
-    void* h_act = nullptr;
-    void* h_obs[2] = { nullptr, nullptr };
+    // host-buffer paths (gpd_step_host / gpd_step_mirror): device staging, allocated lazily and all-or-nothing
+    void* h_act = nullptr;            // actions
+    void* h_obs[2] = { nullptr, nullptr };   // internal observation ping-pong: [obs | reward | terminated | truncated] each
     float* h_tkin = nullptr;
+    uint8_t* h_mask = nullptr;        // persistent reset mask
     int h_cur = 0;
     bool h_has_prev = false;
     double* stats_out = nullptr;
+    double* stats_gather = nullptr;   // [nranks][8] for the in-library NCCL all-gather
+    int stats_gather_ranks = 0;
+    void* init_bufs[2] = { nullptr, nullptr };   // current initial-pose arrays (replaced by gpd_set_init_poses)
+    void* target_buf = nullptr;
+    Mirror mir;
     // TMA: one tensor map per observation buffer the caller has passed (2-D [D rows][W floats], box [DPB][(B-1)*4])
     bool tma_ok = false;
     int tma_bytes = 0, tma_bytes_box = 0, tma_edge = 0;
-    std::unordered_map<const void*, CUtensorMap> tmaps, tmaps_edge;
+    std::unordered_map<const void*, TmapEntry> tmaps, tmaps_edge;
+    uint64_t tmap_tick = 0;
     int tma_edge_bytes = 0;
 };
 
-static const CUtensorMap* get_tmap(gpd_sim* s, const void* base, bool edge = false)
+// Tensor maps are cached per observation buffer (trajectory-chained rollouts use one buffer per step, rollout.py); the
+// least recently used entry is evicted beyond GPD_TMAP_CACHE entries.  Returned by value: no pointer into the table escapes.
+enum { GPD_TMAP_CACHE = 1024 };
+static bool get_tmap(gpd_sim* s, const void* base, bool edge, CUtensorMap* out)
 {
     auto& cache = edge ? s->tmaps_edge : s->tmaps;
     auto it = cache.find(base);
-    if (it != cache.end()) return &it->second;
+    if (it != cache.end()) { it->second.tick = ++s->tmap_tick; *out = it->second.tm; return true; }
     encode_tiled_fn enc = get_encode_fn();
-    if (!enc || ((uintptr_t)base & 15)) return nullptr;
-    if (cache.size() > 512) cache.clear();      // trajectory-chained rollouts use one buffer per step (rollout.py)
+    if (!enc || ((uintptr_t)base & 15)) return false;
+    if (cache.size() >= GPD_TMAP_CACHE) {
+        auto victim = cache.begin();
+        for (auto jt = cache.begin(); jt != cache.end(); ++jt)
+            if (jt->second.tick < victim->second.tick) victim = jt;
+        cache.erase(victim);
+    }
     CUtensorMap tm;
     cuuint64_t gdim[2] = { (cuuint64_t)s->W, (cuuint64_t)s->D };
     cuuint64_t gstr[1] = { (cuuint64_t)s->W * 4 };
@@ -99,8 +141,19 @@ static const CUtensorMap* get_tmap(gpd_sim* s, const void* base, bool edge = fal
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return nullptr;
-    return &cache.emplace(base, tm).first->second;
+    if (r != CUDA_SUCCESS) return false;
+    cache.emplace(base, TmapEntry{ tm, ++s->tmap_tick });
+    *out = tm;
+    return true;
+}
+
+// cudaSetDevice only when the calling thread's current device differs (the step path is called ~1e5 times per second)
+static cudaError_t use_device(int dev)
+{
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return e;
+    return cur == dev ? cudaSuccess : cudaSetDevice(dev);
 }
 
 static int action_width(int act)
@@ -191,13 +244,40 @@ static int upload_init(gpd_sim* s, StepArgs<R>& a, const double* xyz, const doub
         hp[k].x = (R)xyz[3 * k]; hp[k].y = (R)xyz[3 * k + 1]; hp[k].z = (R)xyz[3 * k + 2]; hp[k].w = (R)0;
         hq[k].x = (R)q[0]; hq[k].y = (R)q[1]; hq[k].z = (R)q[2]; hq[k].w = (R)q[3];
     }
+    // the previous arrays may still be read by kernels in flight on any stream: drain the device, then replace them
     V* dp = nullptr; V* dq = nullptr;
-    int rc;
-    if ((rc = dev_alloc(s, &dp, (size_t)n, false))) return rc;
-    if ((rc = dev_alloc(s, &dq, (size_t)n, false))) return rc;
-    CU(cudaMemcpy(dp, hp.data(), sizeof(V) * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dq, hq.data(), sizeof(V) * n, cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMalloc((void**)&dp, sizeof(V) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dq, sizeof(V) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dp, hp.data(), sizeof(V) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dq, hq.data(), sizeof(V) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(dp); cudaFree(dq);
+        return fail(GPD_ERR_ALLOC, "initial-pose upload failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(s->init_bufs[0]); cudaFree(s->init_bufs[1]);
+    s->init_bufs[0] = dp; s->init_bufs[1] = dq;
     a.p.init_pos = dp; a.p.init_quat = dq; a.init_per_env = per_env ? 1 : 0;
+    return GPD_OK;
+}
+
+// HoverAviary.TARGET_POS (HoverAviary.py:51) / MultiHoverAviary.TARGET_POS = INIT_XYZS + [0,0,1/(i+1)] (MultiHoverAviary.py:71):
+// [N][3] shared by every env, or [E][N][3] when the envs start from their own poses.
+template <typename R>
+static int upload_targets(gpd_sim* s, StepArgs<R>& a, const double* t, int per_env)
+{
+    using V = typename Vec4<R>::type;
+    int64_t n = per_env ? s->D : s->cfg.num_drones;
+    std::vector<V> ht((size_t)n);
+    for (int64_t k = 0; k < n; ++k) { ht[k].x = (R)t[3 * k]; ht[k].y = (R)t[3 * k + 1]; ht[k].z = (R)t[3 * k + 2]; ht[k].w = (R)0; }
+    V* dt_ = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dt_, sizeof(V) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dt_, ht.data(), sizeof(V) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(dt_); return fail(GPD_ERR_ALLOC, "target upload failed: %s", cudaGetErrorString(e)); }
+    cudaFree(s->target_buf);
+    s->target_buf = dt_;
+    a.p.target = dt_; a.target_per_env = per_env ? 1 : 0;
     return GPD_OK;
 }
 
@@ -206,7 +286,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
 {
     using V = typename Vec4<R>::type;
     const gpd_config& c = s->cfg;
-    memset(&a, 0, sizeof a);
+    memset((void*)&a, 0, sizeof a);
     a.D = s->D; a.E = c.num_envs; a.N = c.num_drones; a.S = s->S; a.A = s->A; a.B = s->B; a.W = s->W;
     a.env_kind = c.env_kind; a.action_type = c.action_type; a.phy = c.physics_flags; a.auto_reset = c.auto_reset;
     a.dt = (R)(1.0 / c.pyb_freq); a.ctrl_dt = (R)(1.0 / c.ctrl_freq); a.speed_limit = (R)c.speed_limit;
@@ -253,15 +333,14 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
         CU(cudaMemcpy(slots, init.data(), init.size() * sizeof(StatSlot), cudaMemcpyHostToDevice));
         a.p.ep_ret = er; a.p.stat_slots = slots;
     }
-    // targets
-    std::vector<V> ht((size_t)c.num_drones);
-    for (int k = 0; k < c.num_drones; ++k) {
-        ht[k].x = (R)s->target_host[3 * k]; ht[k].y = (R)s->target_host[3 * k + 1]; ht[k].z = (R)s->target_host[3 * k + 2]; ht[k].w = (R)0;
+    if ((rc = upload_targets(s, a, s->target_host.data(), 0))) return rc;
+    {   // per-CTA step sequencing (see ld_acquire_gpu in gpd_kernels.cuh): one 32-byte slot per CTA
+        uint32_t* seq = nullptr;
+        if ((rc = dev_alloc(s, &seq, (size_t)s->lc.grid * 8))) return rc;
+        a.tile_seq = seq;
+        const char* ev = getenv("GPD_TILE_DEP");
+        a.tile_dep = ev ? (atoi(ev) ? 1 : 0) : 1;
     }
-    V* dt_ = nullptr;
-    if ((rc = dev_alloc(s, &dt_, (size_t)c.num_drones, false))) return rc;
-    CU(cudaMemcpy(dt_, ht.data(), sizeof(V) * c.num_drones, cudaMemcpyHostToDevice));
-    a.p.target = dt_;
     a.DPB = s->dpb;
     a.copy_threads = s->copy_threads;
     a.tma_bytes = s->tma_bytes;
@@ -269,7 +348,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     a.tma_edge = s->tma_edge;
     {
         const char* ev = getenv("GPD_PDL_EARLY");
-        a.pdl_trigger_early = ev ? atoi(ev) : (s->lc.grid <= 296 ? 1 : 0);
+        a.pdl_trigger_early = ev ? atoi(ev) : ((a.tile_dep || s->lc.grid <= 296) ? 1 : 0);
         // lean FP32 KIN sims keep ang_v / last_clipped_action only in the observation row (32 B per drone-step less to write)
         const bool rpm_act = c.action_type == GPD_ACT_RPM || c.action_type == GPD_ACT_ONE_D_RPM;
         ev = getenv("GPD_AUX_ALWAYS");
@@ -353,8 +432,10 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         ev = getenv("GPD_TMA_EDGE");
         if (ev) edge_req = atoi(ev) ? 1 : 0;
     }
-    struct Layout { int P, DPB, EPB, threads, copy, tma_edge, tma_bytes_box, tma_edge_bytes, tma_bytes; int64_t grid; size_t smem; };
-    auto make_layout = [&](int P) {
+    struct Layout { int P, DPB, EPB, threads, copy, tma, tma_edge, tma_bytes_box, tma_edge_bytes, tma_bytes; int64_t grid; size_t smem; };
+    int smem_optin = 227 * 1024;
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    auto make_layout = [&](int P, bool allow_tma = true) {
         Layout L{};
         if (N == 1 && P > 128) P = 128;                   // register budget of the single-drone kernels
         L.DPB = P >= N ? (P / N) * N : N;
@@ -365,7 +446,8 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         L.copy = (ctrl || (cfg->precision == GPD_F64 && N > 1 && L.P + 32 > 256)) ? 0 : 32;
         L.threads = L.P + L.copy;
         L.grid = (cfg->num_envs + L.EPB - 1) / L.EPB;
-        const bool tma = tma_on && L.DPB <= 256 && L.copy > 0;
+        const bool tma = allow_tma && tma_on && L.DPB <= 256 && L.copy > 0;
+        L.tma = tma ? 1 : 0;
         // whole-sector split of the row between the drone's thread and TMA (the two old slots the thread needs arrive
         // through two extra 16-byte-wide TMA boxes): no read-modify-write of half-written sectors in ECC HBM.  Measured
         // +10 % at >= 1 M drones, +4 % at 131,072, +2 % at 65,536, -3 % at <= 32,768 (latency-bound: the physics threads
@@ -389,6 +471,8 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 64 : 224;     // downwash: two block barriers per substep favour small CTAs
                                                                 // (512 envs x 64 drones: 17.4 us at 64 threads, 24.1 at 128)
     Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0);
+    // a history tile beyond the shared-memory limit (e.g. 256 drones per env with a 60-slot ring): register-copy path instead
+    if (L.smem > (size_t)smem_optin) L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0, false);
     if (!cfg->threads_per_block) {
         // Wave quantisation: a launch of 1..4 waves pays for its partly filled last wave (MultiHover x2 FP32 at 32,768
         // envs: 512 CTAs on 444 slots = 28.5 us, 293 CTAs on 296 slots = 19.5 us).  Take the block size with the fewest
@@ -411,6 +495,7 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
             for (int P = 64; P <= (N == 1 ? 128 : 256); P += 32) {      // 32-thread CTAs always lose (measured)
                 if (P < N) continue;
                 Layout c = make_layout(P);
+                if (c.smem > (size_t)smem_optin) continue;
                 double f = 0;
                 const int64_t w = waves(c, f);
                 if (getenv("GPD_DEBUG_LAYOUT"))
@@ -428,7 +513,7 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     s->lc.threads = L.threads;
     s->dpb = DPB;
     s->lc.grid = L.grid;
-    s->tma_ok = tma_on && DPB <= 256 && L.copy > 0;
+    s->tma_ok = L.tma != 0;
     s->tma_edge = L.tma_edge;
     s->tma_bytes_box = L.tma_bytes_box;
     s->tma_edge_bytes = L.tma_edge_bytes;
@@ -438,8 +523,12 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
         // parameter fetch overlap the previous kernel's tail); with a full wave the early-resident CTAs all issue their
         // loads at the same instant after the wait and the burst costs more than the overlap gains
+        // With per-CTA step sequencing (GPD_TILE_DEP, the default) there is no whole-grid wait and every step kernel is
+        // launched programmatically: consecutive steps overlap across the kernel boundary at every grid size.
         const char* ev = getenv("GPD_PDL");
-        s->lc.pdl = ev ? atoi(ev) : (s->lc.grid <= 296 ? 1 : 0);
+        const char* td = getenv("GPD_TILE_DEP");
+        const bool tile_dep = td ? atoi(td) != 0 : true;
+        s->lc.pdl = ev ? atoi(ev) : ((tile_dep || s->lc.grid <= 296) ? 1 : 0);
     }
     if (s->lc.grid > 0x7fffffffLL) { delete s; return fail(GPD_ERR_INVALID, "too many envs for one launch"); }
     int rc = cfg->precision == GPD_F64 ? build_args(s, s->a64) : build_args(s, s->a32);
@@ -457,9 +546,12 @@ void gpd_destroy(gpd_sim* s)
 {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
+    cudaDeviceSynchronize();
     for (void* p : s->allocs) cudaFree(p);
     cudaFree(s->h_act); cudaFree(s->h_obs[0]); cudaFree(s->h_obs[1]);
-    cudaFree(s->h_tkin); cudaFree(s->stats_out);
+    cudaFree(s->h_tkin); cudaFree(s->h_mask); cudaFree(s->stats_out); cudaFree(s->stats_gather);
+    cudaFree(s->init_bufs[0]); cudaFree(s->init_bufs[1]); cudaFree(s->target_buf);
+    cudaFree(s->mir.d_kin_t); cudaFree(s->mir.d_full_t);
     delete s;
 }
 
@@ -470,15 +562,23 @@ int gpd_substeps(const gpd_sim* s) { return s ? s->S : fail(GPD_ERR_INVALID, "nu
 int gpd_set_init_poses(gpd_sim* s, const double* xyz, const double* rpy, int per_env)
 {
     if (!s || !xyz || !rpy) return fail(GPD_ERR_INVALID, "gpd_set_init_poses: null argument");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     return s->cfg.precision == GPD_F64 ? upload_init(s, s->a64, xyz, rpy, per_env) : upload_init(s, s->a32, xyz, rpy, per_env);
+}
+
+int gpd_set_targets(gpd_sim* s, const double* target_pos, int per_env)
+{
+    if (!s || !target_pos) return fail(GPD_ERR_INVALID, "gpd_set_targets: null argument");
+    if (s->cfg.env_kind == GPD_ENV_CTRL) return fail(GPD_ERR_INVALID, "the Ctrl env has no target");
+    CU(use_device(s->cfg.device));
+    return s->cfg.precision == GPD_F64 ? upload_targets(s, s->a64, target_pos, per_env) : upload_targets(s, s->a32, target_pos, per_env);
 }
 
 int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* obs_out, void* stream)
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     if (obs_out && obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
@@ -489,59 +589,83 @@ int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* o
         a.reset_mask = env_mask; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out;
         CU(launch_reset<float>(a, s->lc, st));
     }
-    if (obs_out) s->last_obs = obs_out;
+    if (obs_out) { s->last_obs = obs_out; ++s->obs_seq; }
+    return GPD_OK;
+}
+
+static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_out, void* reward, uint8_t* terminated,
+                     uint8_t* truncated, void* terminal_kin, float* kin_t, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    if (!actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step: actions and obs_out are required");
+    if (obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
+    CU(use_device(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tp, to, te;
+    bool have = false;
+    if (s->tma_ok && obs_prev) {
+        have = get_tmap(s, obs_prev, false, &tp) && get_tmap(s, obs_out, false, &to);
+        if (have && s->tma_edge) have = get_tmap(s, obs_prev, true, &te);
+    }
+    const int use_tma = have ? 1 : 0;
+    if (s->cfg.precision == GPD_F64) {
+        StepArgs<double> a = s->a64;
+        a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
+        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
+        a.kin_t = kin_t;
+        CU(launch_step<double>(a, s->lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
+    } else {
+        StepArgs<float> a = s->a32;
+        a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
+        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
+        a.kin_t = kin_t;
+        CU(launch_step<float>(a, s->lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
+    }
+    s->last_obs = obs_out;
+    ++s->obs_seq;
     return GPD_OK;
 }
 
 int gpd_step(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_out,
              void* reward, uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream)
 {
-    if (!s) return fail(GPD_ERR_INVALID, "null handle");
-    if (!actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step: actions and obs_out are required");
-    if (obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
-    CU(cudaSetDevice(s->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const CUtensorMap* tp = nullptr;
-    const CUtensorMap* to = nullptr;
-    const CUtensorMap* te = nullptr;
-    if (s->tma_ok && obs_prev) {
-        tp = get_tmap(s, obs_prev);
-        to = get_tmap(s, obs_out);
-        if (tp) tp = get_tmap(s, obs_prev);     // re-fetch: the second insertion may have rehashed the table
-        if (s->tma_edge) te = get_tmap(s, obs_prev, true);
-    }
-    const int use_tma = (tp && to && (te || !s->tma_edge)) ? 1 : 0;
-    if (s->cfg.precision == GPD_F64) {
-        StepArgs<double> a = s->a64;
-        a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
-        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        CU(launch_step<double>(a, s->lc, tp, to, te, st));
-    } else {
-        StepArgs<float> a = s->a32;
-        a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
-        a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        CU(launch_step<float>(a, s->lc, tp, to, te, st));
-    }
-    s->last_obs = obs_out;
-    return GPD_OK;
+    return step_impl(s, actions, obs_prev, obs_out, reward, terminated, truncated, terminal_kin, nullptr, stream);
 }
 
+// ---- host-buffer paths -------------------------------------------------------------------------------------------------
+struct HostSizes { size_t rs, act_b, obs_b, obs_pad, pack_b, E; };
+static HostSizes host_sizes(const gpd_sim* s)
+{
+    HostSizes z;
+    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
+    z.rs = s->cfg.precision == GPD_F64 ? 8 : 4;
+    z.act_b = (size_t)s->D * s->A * (ctrl ? z.rs : 4);
+    z.obs_b = (size_t)s->D * s->W * (ctrl ? z.rs : 4);
+    z.E = (size_t)s->cfg.num_envs;
+    z.obs_pad = (z.obs_b + 15) & ~size_t(15);     // keeps the reward block aligned for Real stores
+    z.pack_b = z.obs_pad + z.E * z.rs + 2 * z.E;
+    return z;
+}
+
+// Device staging of the host paths, all-or-nothing: a failed allocation leaves the handle exactly as it was.
 static int ensure_host_path(gpd_sim* s)
 {
     if (s->h_obs[0]) return GPD_OK;
-    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
-    const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
-    size_t act_b = (size_t)s->D * s->A * (ctrl ? rs : 4), obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
+    const HostSizes z = host_sizes(s);
     // each ping-pong slot is one packed block [obs | reward | terminated | truncated]: when the caller's host arrays are
     // laid out the same way (the Python facade allocates them so) the whole result travels in ONE device-to-host copy
-    const size_t E = (size_t)s->cfg.num_envs;
-    const size_t obs_pad = (obs_b + 15) & ~size_t(15);     // keeps the reward block aligned for Real stores
-    const size_t pack_b = obs_pad + E * rs + 2 * E;
-    CU(cudaMalloc(&s->h_act, act_b));
-    CU(cudaMalloc(&s->h_obs[0], pack_b));
-    CU(cudaMalloc(&s->h_obs[1], pack_b));
-    CU(cudaMalloc((void**)&s->h_tkin, (size_t)s->D * 12 * sizeof(float)));
-    CU(cudaMemset(s->h_tkin, 0, (size_t)s->D * 12 * sizeof(float)));
+    void *act = nullptr, *o0 = nullptr, *o1 = nullptr, *tk = nullptr, *mk = nullptr;
+    cudaError_t e = cudaMalloc(&act, z.act_b);
+    if (e == cudaSuccess) e = cudaMalloc(&o0, z.pack_b);
+    if (e == cudaSuccess) e = cudaMalloc(&o1, z.pack_b);
+    if (e == cudaSuccess) e = cudaMalloc(&tk, (size_t)s->D * 12 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&mk, z.E);
+    if (e == cudaSuccess) e = cudaMemset(tk, 0, (size_t)s->D * 12 * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(act); cudaFree(o0); cudaFree(o1); cudaFree(tk); cudaFree(mk);
+        return fail(GPD_ERR_ALLOC, "host-path staging allocation failed: %s", cudaGetErrorString(e));
+    }
+    s->h_act = act; s->h_obs[0] = o0; s->h_obs[1] = o1; s->h_tkin = (float*)tk; s->h_mask = (uint8_t*)mk;
     return GPD_OK;
 }
 
@@ -549,34 +673,30 @@ int gpd_step_host(gpd_sim* s, const void* actions, void* obs_out, void* reward,
                   uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream)
 {
     if (!s || !actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step_host: null argument");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     int rc = ensure_host_path(s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
-    const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
-    size_t act_b = (size_t)s->D * s->A * (ctrl ? rs : 4), obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
-    CU(cudaMemcpyAsync(s->h_act, actions, act_b, cudaMemcpyHostToDevice, st));
+    const HostSizes z = host_sizes(s);
+    CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
     int nxt = s->h_cur ^ 1;
-    const size_t E = (size_t)s->cfg.num_envs;
     char* pack = (char*)s->h_obs[nxt];
-    const size_t obs_pad = (obs_b + 15) & ~size_t(15);
-    void* d_rew = pack + obs_pad;
-    uint8_t* d_term = (uint8_t*)(pack + obs_pad + E * rs);
-    uint8_t* d_trunc = d_term + E;
+    void* d_rew = pack + z.obs_pad;
+    uint8_t* d_term = (uint8_t*)(pack + z.obs_pad + z.E * z.rs);
+    uint8_t* d_trunc = d_term + z.E;
     rc = gpd_step(s, s->h_act, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], d_rew, d_term, d_trunc,
                   terminal_kin ? s->h_tkin : nullptr, stream);
     if (rc) return rc;
     s->h_cur = nxt; s->h_has_prev = true;
-    const bool packed = reward == (char*)obs_out + obs_pad && (void*)terminated == (char*)reward + E * rs &&
-                        truncated == terminated + E;
+    const bool packed = reward == (char*)obs_out + z.obs_pad && (void*)terminated == (char*)reward + z.E * z.rs &&
+                        truncated == terminated + z.E;
     if (packed) {
-        CU(cudaMemcpyAsync(obs_out, pack, obs_pad + E * rs + 2 * E, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(obs_out, pack, z.pack_b, cudaMemcpyDeviceToHost, st));
     } else {
-        CU(cudaMemcpyAsync(obs_out, pack, obs_b, cudaMemcpyDeviceToHost, st));
-        if (reward) CU(cudaMemcpyAsync(reward, d_rew, E * rs, cudaMemcpyDeviceToHost, st));
-        if (terminated) CU(cudaMemcpyAsync(terminated, d_term, E, cudaMemcpyDeviceToHost, st));
-        if (truncated) CU(cudaMemcpyAsync(truncated, d_trunc, E, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(obs_out, pack, z.obs_b, cudaMemcpyDeviceToHost, st));
+        if (reward) CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs, cudaMemcpyDeviceToHost, st));
+        if (terminated) CU(cudaMemcpyAsync(terminated, d_term, z.E, cudaMemcpyDeviceToHost, st));
+        if (truncated) CU(cudaMemcpyAsync(truncated, d_trunc, z.E, cudaMemcpyDeviceToHost, st));
     }
     if (terminal_kin) CU(cudaMemcpyAsync(terminal_kin, s->h_tkin, (size_t)s->D * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -586,34 +706,241 @@ int gpd_step_host(gpd_sim* s, const void* actions, void* obs_out, void* reward,
 int gpd_reset_host(gpd_sim* s, const uint8_t* env_mask, void* obs_out, void* stream)
 {
     if (!s || !obs_out) return fail(GPD_ERR_INVALID, "gpd_reset_host: null argument");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     int rc = ensure_host_path(s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool ctrl = s->cfg.env_kind == GPD_ENV_CTRL;
-    const size_t rs = s->cfg.precision == GPD_F64 ? 8 : 4;
-    size_t obs_b = (size_t)s->D * s->W * (ctrl ? rs : 4);
-    uint8_t* dmask = nullptr;
-    if (env_mask) {
-        CU(cudaMalloc((void**)&dmask, (size_t)s->cfg.num_envs));
-        CU(cudaMemcpyAsync(dmask, env_mask, (size_t)s->cfg.num_envs, cudaMemcpyHostToDevice, st));
-    }
+    const HostSizes z = host_sizes(s);
+    if (env_mask) CU(cudaMemcpyAsync(s->h_mask, env_mask, z.E, cudaMemcpyHostToDevice, st));
     int nxt = s->h_cur ^ 1;
-    rc = gpd_reset(s, dmask, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], stream);
-    if (rc == GPD_OK) {
-        s->h_cur = nxt; s->h_has_prev = true;
-        cudaError_t e = cudaMemcpyAsync(obs_out, s->h_obs[nxt], obs_b, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = fail(GPD_ERR_CUDA, "gpd_reset_host copy failed: %s", cudaGetErrorString(e));
+    rc = gpd_reset(s, env_mask ? s->h_mask : nullptr, s->h_has_prev ? s->h_obs[s->h_cur] : nullptr, s->h_obs[nxt], stream);
+    if (rc) return rc;
+    s->h_cur = nxt; s->h_has_prev = true;
+    CU(cudaMemcpyAsync(obs_out, s->h_obs[nxt], z.obs_b, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GPD_OK;
+}
+
+// ---- host mirror (see struct Mirror) -----------------------------------------------------------------------------------
+int gpd_mirror_alloc(int64_t rows, int64_t row_len, float** log_out)
+{
+    if (!log_out || rows < 1 || row_len < 1) return fail(GPD_ERR_INVALID, "gpd_mirror_alloc: bad argument");
+    *log_out = nullptr;
+    void* p = nullptr;
+    const size_t bytes = (size_t)rows * (size_t)row_len * sizeof(float);
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? GPD_ERR_NO_DEVICE : GPD_ERR_ALLOC,
+                    "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    memset(p, 0, bytes);
+    *log_out = (float*)p;
+    return GPD_OK;
+}
+
+int gpd_mirror_free(float* log)
+{
+    if (log) CU(cudaFreeHost(log));
+    return GPD_OK;
+}
+
+int gpd_mirror_attach(gpd_sim* s, float* log, int64_t rows, int64_t row_len, int64_t col0)
+{
+    if (!s || !log) return fail(GPD_ERR_INVALID, "gpd_mirror_attach: null argument");
+    if (s->cfg.env_kind == GPD_ENV_CTRL)
+        return fail(GPD_ERR_INVALID, "the Ctrl observation has no action ring: use gpd_step_host (every byte of it is device-computed)");
+    if (rows < s->W + s->A || col0 < 0 || row_len < col0 + s->D)
+        return fail(GPD_ERR_INVALID, "gpd_mirror_attach: the log needs at least W + A = %d rows and col0 + D = %lld columns",
+                    s->W + s->A, (long long)(col0 + s->D));
+    CU(use_device(s->cfg.device));
+    int rc = ensure_host_path(s);
+    if (rc) return rc;
+    if (!s->mir.d_kin_t) {
+        void* k = nullptr;
+        cudaError_t e = cudaMalloc(&k, (size_t)12 * s->D * sizeof(float));
+        if (e != cudaSuccess) return fail(GPD_ERR_ALLOC, "cudaMalloc failed: %s", cudaGetErrorString(e));
+        s->mir.d_kin_t = (float*)k;
     }
-    if (dmask) cudaFree(dmask);
-    return rc;
+    Mirror& m = s->mir;
+    m.log = log; m.rows = rows; m.ld = row_len; m.col0 = col0;
+    m.row = 0; m.valid = false; m.pending = false;
+    return GPD_OK;
+}
+
+int64_t gpd_mirror_row(const gpd_sim* s)
+{
+    if (!s || !s->mir.log) return fail(GPD_ERR_INVALID, "no host mirror attached");
+    return s->mir.row;
+}
+
+// device [nrows][D] (contiguous) -> log rows [row0, row0 + nrows), this handle's columns
+static cudaError_t mirror_rows_d2h(gpd_sim* s, int64_t row0, const float* d_src, int nrows, cudaStream_t st)
+{
+    Mirror& m = s->mir;
+    float* dst = m.log + row0 * m.ld + m.col0;
+    if (m.ld == s->D)
+        return cudaMemcpyAsync(dst, d_src, (size_t)nrows * s->D * sizeof(float), cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(dst, (size_t)m.ld * sizeof(float), d_src, (size_t)s->D * sizeof(float), (size_t)s->D * sizeof(float),
+                             (size_t)nrows, cudaMemcpyDeviceToHost, st);
+}
+
+// Rebuilds the window rows [row, row + W) from a device observation (or zeroes the ring when there is none yet).
+static int mirror_refresh(gpd_sim* s, const void* d_obs, int64_t row, cudaStream_t st)
+{
+    Mirror& m = s->mir;
+    if (!d_obs) {       // no observation yet: all-zero ring (BaseRLAviary.py:153-154); the kin rows are written by the step
+        CU(cudaStreamSynchronize(st));
+        for (int64_t r = row; r < row + s->W; ++r) memset(m.log + r * m.ld + m.col0, 0, (size_t)s->D * sizeof(float));
+        return GPD_OK;
+    }
+    if (!m.d_full_t) {
+        void* f = nullptr;
+        cudaError_t e = cudaMalloc(&f, (size_t)s->W * s->D * sizeof(float));
+        if (e != cudaSuccess) return fail(GPD_ERR_ALLOC, "cudaMalloc failed: %s", cudaGetErrorString(e));
+        m.d_full_t = (float*)f;
+    }
+    CU(launch_transpose_cols((const float*)d_obs, s->D, s->W, 0, s->W, m.d_full_t, s->D, st));
+    CU(mirror_rows_d2h(s, row, m.d_full_t, s->W, st));
+    return GPD_OK;
+}
+
+// newest action, host -> host: actions[d][A] into the A log rows that follow the window (transposed; streaming stores)
+static void mirror_write_action(const gpd_sim* s, const float* act, int64_t row)
+{
+    const Mirror& m = s->mir;
+    const int64_t D = s->D;
+    const int A = s->A;
+    float* r0 = m.log + row * m.ld + m.col0;
+    if (A == 4 && ((uintptr_t)act & 15) == 0 && ((uintptr_t)r0 & 15) == 0 && (m.ld & 3) == 0) {
+        float *q0 = r0, *q1 = r0 + m.ld, *q2 = r0 + 2 * m.ld, *q3 = r0 + 3 * m.ld;
+        int64_t d = 0;
+        for (; d + 4 <= D; d += 4) {
+            __m128 a0 = _mm_load_ps(act + 4 * d), a1 = _mm_load_ps(act + 4 * d + 4), a2 = _mm_load_ps(act + 4 * d + 8),
+                   a3 = _mm_load_ps(act + 4 * d + 12);
+            _MM_TRANSPOSE4_PS(a0, a1, a2, a3);
+            _mm_stream_ps(q0 + d, a0); _mm_stream_ps(q1 + d, a1); _mm_stream_ps(q2 + d, a2); _mm_stream_ps(q3 + d, a3);
+        }
+        for (; d < D; ++d) { q0[d] = act[4 * d]; q1[d] = act[4 * d + 1]; q2[d] = act[4 * d + 2]; q3[d] = act[4 * d + 3]; }
+        _mm_sfence();
+        return;
+    }
+    for (int k = 0; k < A; ++k) {
+        float* q = r0 + (int64_t)k * m.ld;
+        for (int64_t d = 0; d < D; ++d) q[d] = act[d * A + k];
+    }
+}
+
+int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_prev, void* d_obs_out, void* reward,
+                          uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream)
+{
+    if (!s || !actions) return fail(GPD_ERR_INVALID, "gpd_step_mirror: null argument");
+    Mirror& m = s->mir;
+    if (!m.log) return fail(GPD_ERR_INVALID, "gpd_step_mirror: no host mirror attached (gpd_mirror_attach)");
+    if (m.pending) return fail(GPD_ERR_INVALID, "gpd_step_mirror_begin: the previous step was not completed (gpd_step_mirror_end)");
+    CU(use_device(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const HostSizes z = host_sizes(s);
+    const bool internal = d_obs_out == nullptr;      // NULL: the handle's own observation ping-pong
+    int nxt = s->h_cur ^ 1;
+    if (internal) {
+        d_obs_prev = s->h_has_prev ? s->h_obs[s->h_cur] : nullptr;
+        d_obs_out = s->h_obs[nxt];
+    }
+    // window maintenance: out of room -> back to row 0 (compaction); stale (the device chain moved without the mirror) -> in place
+    const bool in_sync = m.valid && m.synced_seq == s->obs_seq && m.synced_obs == d_obs_prev;
+    const bool no_room = m.row + s->A + s->W > m.rows;
+    if (no_room || !in_sync) {
+        if (no_room) m.row = 0;
+        int rc = mirror_refresh(s, d_obs_prev, m.row, st);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
+    char* pack = (char*)s->h_obs[nxt] + z.obs_pad;    // reward / flags staging lives behind the internal observation slot
+    void* d_rew = pack;
+    uint8_t* d_term = (uint8_t*)(pack + z.E * z.rs);
+    uint8_t* d_trunc = d_term + z.E;
+    int rc = step_impl(s, s->h_act, d_obs_prev, d_obs_out, d_rew, d_term, d_trunc, terminal_kin ? s->h_tkin : nullptr, m.d_kin_t, stream);
+    if (rc) return rc;
+    if (internal) { s->h_cur = nxt; s->h_has_prev = true; }
+    // what the device computed: 12 kin rows into the slid window, reward and flags
+    CU(mirror_rows_d2h(s, m.row + s->A, m.d_kin_t, 12, st));
+    const bool packed = reward && (void*)terminated == (char*)reward + z.E * z.rs && truncated == terminated + z.E;
+    if (packed) {
+        CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs + 2 * z.E, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (reward) CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs, cudaMemcpyDeviceToHost, st));
+        if (terminated) CU(cudaMemcpyAsync(terminated, d_term, z.E, cudaMemcpyDeviceToHost, st));
+        if (truncated) CU(cudaMemcpyAsync(truncated, d_trunc, z.E, cudaMemcpyDeviceToHost, st));
+    }
+    if (terminal_kin) CU(cudaMemcpyAsync(terminal_kin, s->h_tkin, (size_t)s->D * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    m.pending = true;
+    m.pending_obs = d_obs_out;
+    m.pending_actions = (const float*)actions;
+    return GPD_OK;
+}
+
+int gpd_step_mirror_end(gpd_sim* s, int64_t* first_row, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    Mirror& m = s->mir;
+    if (!m.pending) return fail(GPD_ERR_INVALID, "gpd_step_mirror_end without gpd_step_mirror_begin");
+    m.pending = false;
+    m.valid = false;
+    // what the host already has: its own action, transposed into the newest ring rows while the device works
+    mirror_write_action(s, m.pending_actions, m.row + s->W);
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    m.row += s->A;
+    m.valid = true; m.synced_seq = s->obs_seq; m.synced_obs = m.pending_obs;
+    if (first_row) *first_row = m.row;
+    return GPD_OK;
+}
+
+int gpd_step_mirror(gpd_sim* s, const void* actions, const void* d_obs_prev, void* d_obs_out, void* reward,
+                    uint8_t* terminated, uint8_t* truncated, void* terminal_kin, int64_t* first_row, void* stream)
+{
+    int rc = gpd_step_mirror_begin(s, actions, d_obs_prev, d_obs_out, reward, terminated, truncated, terminal_kin, stream);
+    if (rc) return rc;
+    return gpd_step_mirror_end(s, first_row, stream);
+}
+
+int gpd_reset_mirror(gpd_sim* s, const uint8_t* env_mask, const void* d_obs_prev, void* d_obs_out, int64_t* first_row, void* stream)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    Mirror& m = s->mir;
+    if (!m.log) return fail(GPD_ERR_INVALID, "gpd_reset_mirror: no host mirror attached (gpd_mirror_attach)");
+    if (m.pending) return fail(GPD_ERR_INVALID, "gpd_reset_mirror: a step is in flight (gpd_step_mirror_end)");
+    CU(use_device(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const HostSizes z = host_sizes(s);
+    const bool internal = d_obs_out == nullptr;
+    int nxt = s->h_cur ^ 1;
+    if (internal) {
+        d_obs_prev = s->h_has_prev ? s->h_obs[s->h_cur] : nullptr;
+        d_obs_out = s->h_obs[nxt];
+    }
+    const bool in_sync = m.valid && m.synced_seq == s->obs_seq && m.synced_obs == d_obs_prev;
+    if (env_mask) CU(cudaMemcpyAsync(s->h_mask, env_mask, z.E, cudaMemcpyHostToDevice, st));
+    int rc = gpd_reset(s, env_mask ? s->h_mask : nullptr, d_obs_prev, d_obs_out, stream);
+    if (rc) return rc;
+    if (internal) { s->h_cur = nxt; s->h_has_prev = true; }
+    m.valid = false;
+    if (in_sync) {      // the ring survives a reset (BaseRLAviary.py:153-154): only the 12 kin rows change, the window does not move
+        CU(launch_transpose_cols((const float*)d_obs_out, s->D, s->W, 0, 12, m.d_kin_t, s->D, st));
+        CU(mirror_rows_d2h(s, m.row, m.d_kin_t, 12, st));
+    } else {
+        if (m.row + s->W > m.rows) m.row = 0;
+        rc = mirror_refresh(s, d_obs_out, m.row, st);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(st));
+    m.valid = true; m.synced_seq = s->obs_seq; m.synced_obs = d_obs_out;
+    if (first_row) *first_row = m.row;
+    return GPD_OK;
 }
 
 int gpd_get_state(gpd_sim* s, void* state20, void* rpy_rates, void* pid_state, int32_t* step_counter, void* stream)
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     if (s->cfg.precision == GPD_F64)
         CU(launch_get_state<double>(s->a64, (const float*)s->last_obs, (double*)state20, (double*)rpy_rates, (double*)pid_state, step_counter, (cudaStream_t)stream));
     else
@@ -625,6 +952,7 @@ int gpd_note_latest_obs(gpd_sim* s, const void* obs)
 {
     if (!s || !obs) return fail(GPD_ERR_INVALID, "gpd_note_latest_obs: null argument");
     s->last_obs = obs;
+    ++s->obs_seq;                 // the caller replaced the latest observation: a host mirror must be rebuilt from it
     return GPD_OK;
 }
 
@@ -632,7 +960,7 @@ int gpd_set_state(gpd_sim* s, const void* state20, const void* rpy_rates, const 
                   const int32_t* step_counter, void* stream)
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     if (s->cfg.precision == GPD_F64)
         CU(launch_set_state<double>(s->a64, (const double*)state20, (const double*)rpy_rates, (const double*)pid_state, step_counter, (cudaStream_t)stream));
     else
@@ -648,7 +976,7 @@ int gpd_pid_compute(int device, int precision, const gpd_pid_params* pid, int64_
     if (!pid || !cur_pos || !cur_quat || !cur_vel || !target_pos || !pid_state || !rpm_out || n < 0)
         return fail(GPD_ERR_INVALID, "gpd_pid_compute: null argument");
     if (n == 0) return GPD_OK;
-    CU(cudaSetDevice(device));
+    CU(use_device(device));
     if (precision == GPD_F64) {
         DevPid<double> c; fill_pid(*pid, c);
         CU(launch_pid<double>(c, n, control_timestep, (const double*)cur_pos, (const double*)cur_quat, (const double*)cur_vel,
@@ -670,7 +998,7 @@ int gpd_force_ground_effect(int device, int precision, const gpd_drone_params* d
 {
     if (!d || !rpm || !pos || !quat || !out || n < 0) return fail(GPD_ERR_INVALID, "gpd_force_ground_effect: null argument");
     if (n == 0) return GPD_OK;
-    CU(cudaSetDevice(device));
+    CU(use_device(device));
     if (precision == GPD_F64) { DevDrone<double> P; fill_drone(*d, P);
         CU(launch_ground_effect<double>(P, n, (const double*)rpm, (const double*)pos, (const double*)quat, (double*)out, applied, (cudaStream_t)stream)); }
     else { DevDrone<float> P; fill_drone(*d, P);
@@ -683,7 +1011,7 @@ int gpd_force_drag(int device, int precision, const gpd_drone_params* d, int64_t
 {
     if (!d || !rpm || !quat || !vel || !out || n < 0) return fail(GPD_ERR_INVALID, "gpd_force_drag: null argument");
     if (n == 0) return GPD_OK;
-    CU(cudaSetDevice(device));
+    CU(use_device(device));
     if (precision == GPD_F64) { DevDrone<double> P; fill_drone(*d, P);
         CU(launch_drag<double>(P, n, (const double*)rpm, (const double*)quat, (const double*)vel, (double*)out, (cudaStream_t)stream)); }
     else { DevDrone<float> P; fill_drone(*d, P);
@@ -696,7 +1024,7 @@ int gpd_force_downwash(int device, int precision, const gpd_drone_params* d, int
 {
     if (!d || !pos || !out || num_envs < 0 || num_drones < 1) return fail(GPD_ERR_INVALID, "gpd_force_downwash: bad argument");
     if (num_envs == 0) return GPD_OK;
-    CU(cudaSetDevice(device));
+    CU(use_device(device));
     if (precision == GPD_F64) { DevDrone<double> P; fill_drone(*d, P);
         CU(launch_downwash<double>(P, num_envs, num_drones, (const double*)pos, (double*)out, (cudaStream_t)stream)); }
     else { DevDrone<float> P; fill_drone(*d, P);
@@ -722,7 +1050,7 @@ int gpd_rollout_pid(gpd_sim* s, int32_t n_ctrl_steps, const void* waypoints, int
     if (s->cfg.env_kind != GPD_ENV_CTRL) return fail(GPD_ERR_INVALID, "gpd_rollout_pid needs the Ctrl env");
     if (s->cfg.drone.model == GPD_RACE) return fail(GPD_ERR_INVALID, "DSLPIDControl requires CF2X or CF2P");
     if (s->cfg.physics_flags & GPD_PHY_DW) return fail(GPD_ERR_INVALID, "gpd_rollout_pid does not support downwash");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     if (s->cfg.precision == GPD_F64)
         CU(launch_rollout_pid<double>(s->a64, n_ctrl_steps, (const double*)waypoints, n_wp, wp_counters, (double*)action, (cudaStream_t)stream));
     else
@@ -733,7 +1061,7 @@ int gpd_rollout_pid(gpd_sim* s, int32_t n_ctrl_steps, const void* waypoints, int
 int gpd_count_nonfinite(gpd_sim* s, long long* out_host, void* stream)
 {
     if (!s || !out_host) return fail(GPD_ERR_INVALID, "gpd_count_nonfinite: null argument");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* cnt = (unsigned long long*)s->stats_out;       // reuse the 64-byte scratch
     CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
@@ -746,17 +1074,118 @@ int gpd_count_nonfinite(gpd_sim* s, long long* out_host, void* stream)
     return GPD_OK;
 }
 
-int gpd_episode_stats(gpd_sim* s, double out[8], int clear, void* stream)
+// ---- NCCL, bound at run time: the library never links against libnccl; a process that passes a communicator has it loaded ----
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+static const NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy the process already uses (e.g. torch's)
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.CommCount = (decltype(api.CommCount))dlsym(h, "ncclCommCount");
+    api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.CommCount && api.AllGather && api.GetErrorString;
+    return api.ok ? &api : nullptr;
+}
+
+#define NC(api, call)                                                                                    \
+    do {                                                                                                 \
+        ncclResult_t _r = (call);                                                                        \
+        if (_r != ncclSuccess) return fail(GPD_ERR_CUDA, "%s failed: %s", #call, (api)->GetErrorString(_r)); \
+    } while (0)
+
+int gpd_nccl_unique_id(char id_out[GPD_NCCL_UNIQUE_ID_BYTES])
+{
+    if (!id_out) return fail(GPD_ERR_INVALID, "gpd_nccl_unique_id: null argument");
+    const NcclApi* n = nccl_api();
+    if (!n) return fail(GPD_ERR_INVALID, "libnccl.so.2 could not be loaded: %s", dlerror());
+    static_assert(sizeof(ncclUniqueId) == GPD_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(n, n->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return GPD_OK;
+}
+
+int gpd_nccl_comm_init(const char id[GPD_NCCL_UNIQUE_ID_BYTES], int rank, int world_size, int device, void** comm_out)
+{
+    if (!id || !comm_out || world_size < 1 || rank < 0 || rank >= world_size) return fail(GPD_ERR_INVALID, "gpd_nccl_comm_init: bad argument");
+    *comm_out = nullptr;
+    const NcclApi* n = nccl_api();
+    if (!n) return fail(GPD_ERR_INVALID, "libnccl.so.2 could not be loaded: %s", dlerror());
+    CU(use_device(device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclComm_t c = nullptr;
+    NC(n, n->CommInitRank(&c, world_size, uid, rank));
+    *comm_out = c;
+    return GPD_OK;
+}
+
+int gpd_nccl_comm_destroy(void* comm)
+{
+    if (!comm) return GPD_OK;
+    const NcclApi* n = nccl_api();
+    if (!n) return fail(GPD_ERR_INVALID, "libnccl.so.2 could not be loaded");
+    NC(n, n->CommDestroy((ncclComm_t)comm));
+    return GPD_OK;
+}
+
+int gpd_episode_stats(gpd_sim* s, double out[8], int clear, void* nccl_comm, void* stream)
 {
     if (!s || !out) return fail(GPD_ERR_INVALID, "gpd_episode_stats: null argument");
     for (int k = 0; k < 8; ++k) out[k] = 0.0;
     if (!s->cfg.auto_reset) return fail(GPD_ERR_INVALID, "episode statistics are kept only with auto_reset");
-    CU(cudaSetDevice(s->cfg.device));
+    CU(use_device(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
     StatSlot* slots = s->cfg.precision == GPD_F64 ? s->a64.p.stat_slots : s->a32.p.stat_slots;
-    CU(launch_stats(slots, s->lc.grid, s->stats_out, clear, slots, (cudaStream_t)stream));
-    CU(cudaMemcpyAsync(out, s->stats_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(launch_stats(slots, s->lc.grid, s->stats_out, clear, slots, st));
+    const double* result = s->stats_out;
+    if (nccl_comm) {    // job-wide: ONE collective (all-gather of the 8 doubles of every rank) + a rank-order combine on the device
+        const NcclApi* n = nccl_api();
+        if (!n) return fail(GPD_ERR_INVALID, "a communicator was passed but libnccl.so.2 could not be loaded");
+        int nranks = 0;
+        NC(n, n->CommCount((ncclComm_t)nccl_comm, &nranks));
+        if (nranks > s->stats_gather_ranks) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(s->stats_gather);
+            s->stats_gather = nullptr; s->stats_gather_ranks = 0;
+            CU(cudaMalloc((void**)&s->stats_gather, (size_t)(nranks + 1) * 8 * sizeof(double)));
+            s->stats_gather_ranks = nranks;
+        }
+        NC(n, n->AllGather(s->stats_out, s->stats_gather, 8, ncclFloat64, (ncclComm_t)nccl_comm, st));
+        double* combined = s->stats_gather + (size_t)nranks * 8;
+        CU(launch_stats_combine(s->stats_gather, nranks, combined, st));
+        result = combined;
+    }
+    CU(cudaMemcpyAsync(out, result, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (out[0] == 0.0) { out[4] = 0.0; out[5] = 0.0; }
+    return GPD_OK;
+}
+
+int gpd_adjacency(gpd_sim* s, double neighbourhood_radius, void* out, void* stream)
+{
+    if (!s || !out) return fail(GPD_ERR_INVALID, "gpd_adjacency: null argument");
+    CU(use_device(s->cfg.device));
+    if (s->cfg.precision == GPD_F64) CU(launch_adjacency<double>(s->a64, neighbourhood_radius, (double*)out, (cudaStream_t)stream));
+    else CU(launch_adjacency<float>(s->a32, (float)neighbourhood_radius, (float*)out, (cudaStream_t)stream));
     return GPD_OK;
 }
 

@@ -44,6 +44,62 @@ __global__ void stats_clear_kernel(StatSlot* __restrict__ slots, int64_t nslots)
     s.mn = 0x7fffffff; s.mx = (int32_t)0x80000000;
 }
 
+// ============================================================================================
+// Host mirror support: columns [j0, j1) of a row-major observation [D][W] -> feature-major out[(j - j0) * ld + d].
+// Used when the host copy of the observation window is (re)built from the device chain: after a reset, when the
+// window reaches the end of the host log (compaction) and when the mirror went stale (tensor-path steps in between).
+// 32 x 32 tiles through padded shared memory: both sides coalesced.
+// ============================================================================================
+__global__ void __launch_bounds__(256)
+transpose_cols_kernel(const float* __restrict__ obs, int64_t D, int W, int j0, int j1, float* __restrict__ out, int64_t ld)
+{
+    __shared__ float tile[32][33];
+    const int64_t d0 = (int64_t)blockIdx.x * 32;
+    const int c0 = j0 + (int)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t d = d0 + r;
+        const int j = c0 + tx;
+        tile[r][tx] = (d < D && j < j1) ? obs[d * W + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int j = c0 + r;
+        const int64_t d = d0 + tx;
+        if (j < j1 && d < D) out[(int64_t)(j - j0) * ld + d] = tile[tx][r];
+    }
+}
+
+cudaError_t launch_transpose_cols(const float* obs, int64_t D, int W, int j0, int j1, float* out, int64_t ld, cudaStream_t st)
+{
+    if (j1 <= j0 || D <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((D + 31) / 32), (unsigned)((j1 - j0 + 31) / 32));
+    transpose_cols_kernel<<<grid, 256, 0, st>>>(obs, D, W, j0, j1, out, ld);
+    return cudaGetLastError();
+}
+
+// job-wide statistics from the all-gathered per-rank vectors {episodes, ret, len, ret^2, min, max, env_steps, terminated}:
+// sums in rank order (deterministic), min/max over the ranks that finished at least one episode
+__global__ void stats_combine_kernel(const double* __restrict__ g, int nranks, double* __restrict__ out8)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double acc[8] = { 0, 0, 0, 0, 1e300, -1e300, 0, 0 };
+    for (int r = 0; r < nranks; ++r) {
+        const double* v = g + (size_t)r * 8;
+        acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3]; acc[6] += v[6]; acc[7] += v[7];
+        if (v[0] > 0) { acc[4] = fmin(acc[4], v[4]); acc[5] = fmax(acc[5], v[5]); }
+    }
+    for (int j = 0; j < 8; ++j) out8[j] = acc[j];
+}
+
+cudaError_t launch_stats_combine(const double* gathered, int nranks, double* out8, cudaStream_t st)
+{
+    stats_combine_kernel<<<1, 32, 0, st>>>(gathered, nranks, out8);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stats(const StatSlot* slots, int64_t nslots, double* out8, int clear, StatSlot* slots_mut, cudaStream_t st)
 {
     stats_reduce_kernel<<<1, 256, 0, st>>>(slots, nslots, out8);

@@ -9,6 +9,8 @@
 
 namespace gpd {
 
+enum { GPD_MAX_DEVICES = 64 };
+
 // per-block episode-statistics partials: sums {episodes, return, length, return^2, env_steps, terminated} and the
 // min/max episode return as order-preserving int32 images of float32
 struct StatSlot {
@@ -70,7 +72,7 @@ struct SimPtrs {
     StatSlot* stat_slots;   // [grid] per-block statistics partials (fire-and-forget atomics, no contention)
     const typename Vec4<R>::type* init_pos;   // [N] or [D]  (xyz, 0)
     const typename Vec4<R>::type* init_quat;  // [N] or [D]
-    const typename Vec4<R>::type* target;     // [N] (xyz, 0)
+    const typename Vec4<R>::type* target;     // [N] or [D] (xyz, 0)
 };
 
 template <typename R>
@@ -100,6 +102,10 @@ struct StepArgs {
     float* terminal_kin;
     const uint8_t* reset_mask;   // reset kernel only
     unsigned long long* timeline; // diagnostics: [grid][8] phase timestamps (ns, %globaltimer) or nullptr
+    float* kin_t;           // host-mirror export: feature-major copy [12][D] of the kinematic observation part, or nullptr
+    uint32_t* tile_seq;     // per-CTA step sequencing [grid][8]: word 0 = steps claimed, word 1 = steps completed (tile_dep)
+    int32_t tile_dep;       // 1: a CTA waits only for ITS OWN tile's previous step (per-CTA flag) instead of the whole grid
+    int32_t target_per_env; // 1: p.target holds D entries (per-env MultiHover targets), else N
     SimPtrs<R> p;
     DevDrone<R> drone;
     DevPid<R> pid;
@@ -135,6 +141,7 @@ template <typename R> cudaError_t launch_drag(const DevDrone<R>& d, int64_t n, c
                                               const R* vel, R* out, cudaStream_t st);
 template <typename R> cudaError_t launch_downwash(const DevDrone<R>& d, int64_t E, int N, const R* pos, R* out,
                                                   cudaStream_t st);
+template <typename R> cudaError_t launch_adjacency(const StepArgs<R>& a, R radius, R* out, cudaStream_t st);
 template <typename R> cudaError_t launch_nonfinite(const StepArgs<R>& a, unsigned long long* out, cudaStream_t st);
 template <typename R> cudaError_t launch_rollout_pid(const StepArgs<R>& a, int n_steps, const R* waypoints, int n_wp,
                                                      int32_t* wp_counters, R* action, cudaStream_t st);

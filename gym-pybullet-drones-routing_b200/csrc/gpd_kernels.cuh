@@ -31,6 +31,23 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Per-CTA step sequencing (tile_dep): CTA i of step k+1 depends only on CTA i of step k (same rows, same DPB), so instead
+// of the whole-grid griddepcontrol.wait it acquires its own tile's `completed` counter.  The step kernel is launched with
+// programmatic stream serialization and releases its dependents as soon as every CTA has CLAIMED its sequence number; a
+// dependent grid therefore starts only after every CTA of every earlier step kernel of the stream has started (and claimed),
+// which orders the claims and excludes deadlock: a spinning CTA only ever waits for a CTA that is already resident.
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_inc(uint32_t* p)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long gtime()
 {
     unsigned long long t;
@@ -72,6 +89,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// the bulk store's global writes are complete (not only its shared-memory reads): needed before this CTA publishes its tile
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- shared-memory layout -------------------------------------------------------------
 //   tile  : RL envs with A == 4: TMA box of the action history, DPB x (B-1) float4 (a.tma_bytes)
@@ -278,11 +297,14 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
         else { tp[0] = s.px + dx / dist * R(1); tp[1] = s.py + dy / dist * R(1); tp[2] = s.pz + dz / dist * R(1); }
     } else if (a.action_type == GPD_ACT_VEL) {
         // BaseRLAviary.py:208-223; the unit vector and the speed are float32 expressions in the reference
-        float n = sqrtf(act[0] * act[0] + act[1] * act[1] + act[2] * act[2]);
+        // np.linalg.norm(float32[3]) = sqrt(sdot(x, x)): float32 products, OpenBLAS accumulates the scalar tail in double and
+        // rounds the sum to float32, then a float32 sqrt (checked bit for bit against numpy on 200,000 random vectors)
+        const double sq = (double)__fmul_rn(act[0], act[0]) + (double)__fmul_rn(act[1], act[1]) + (double)__fmul_rn(act[2], act[2]);
+        float n = __fsqrt_rn((float)sq);
         float u0 = 0.f, u1 = 0.f, u2 = 0.f;
-        if (n != 0.f) { u0 = act[0] / n; u1 = act[1] / n; u2 = act[2] / n; }
-        float sp = (float)a.speed_limit * fabsf(act[3]);
-        tv[0] = R(sp * u0); tv[1] = R(sp * u1); tv[2] = R(sp * u2);
+        if (n != 0.f) { u0 = __fdiv_rn(act[0], n); u1 = __fdiv_rn(act[1], n); u2 = __fdiv_rn(act[2], n); }
+        float sp = __fmul_rn((float)a.speed_limit, fabsf(act[3]));
+        tv[0] = R(__fmul_rn(sp, u0)); tv[1] = R(__fmul_rn(sp, u1)); tv[2] = R(__fmul_rn(sp, u2));
         tp[0] = s.px; tp[1] = s.py; tp[2] = s.pz;
         R roll, pitch, yaw;
         quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
@@ -334,13 +356,31 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool run_physics = t < nphys;
 
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 0] = gtime();      // 0: CTA start (params fetched)
-    if (a.pdl_trigger_early) pdl_launch_dependents();
     const bool tma_copy = spec && a.use_tma;
     const bool edge_smem = tma_copy && VEC && a.tma_edge;       // physics threads read the two edge slots from shared memory
     if (tma_copy && t == nphys) mbar_init(&tma_bar, 1);
-    if (edge_smem) __syncthreads();     // the physics threads will wait on the mbarrier the DMA lane just initialised
-    pdl_wait();                         // everything above touched only parameters and shared memory
-    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous kernel complete
+    // this step's action does not depend on the previous step: its load overlaps the sequencing round trip below
+    float4 act_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (VEC) {
+        if (run_physics && active && a.action_type != GPD_ACT_CTRL_RPM && a.action_type != GPD_ACT_CTRL_VEL)
+            act_pre = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
+    }
+    if (a.tile_dep) {
+        if (t == 0) {                   // claim this tile's sequence number and look at its completed count in one round trip
+            uint32_t* seq = a.tile_seq + (int64_t)blockIdx.x * 8;
+            const uint32_t done0 = ld_acquire_gpu(seq + 1);
+            const uint32_t mine = atomicAdd(seq, 1u);          // steps claimed before this one
+            if (done0 != mine)
+                while (ld_acquire_gpu(seq + 1) != mine) __nanosleep(32);
+        }
+        __syncthreads();                // the claim is performed: dependents may start; the tile's previous step is visible
+        if (a.pdl_trigger_early) pdl_launch_dependents();
+    } else {
+        if (a.pdl_trigger_early) pdl_launch_dependents();
+        if (edge_smem) __syncthreads(); // the physics threads will wait on the mbarrier the DMA lane just initialised
+        pdl_wait();                     // everything above touched only parameters and shared memory
+    }
+    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous step of this tile complete
 
     if (!ctrl && !tma_copy)             // no TMA for this row shape (A = 3 or 1) or no previous observation: every thread
         copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
@@ -348,6 +388,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     if (spec && !run_physics) {
         if (tma_copy && !VEC) {         // A = 1..3: TMA load of the whole old ring, shifted write-out by the 32 lanes
             if (t == nphys) {
+                if (a.tile_dep) fence_proxy_async_global();
                 mbar_expect_tx(&tma_bar, (uint32_t)a.tma_bytes_box);
                 tma_load_2d(smem_raw, &tm_prev, 12, (int)row0, &tma_bar);
             }
@@ -365,6 +406,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 // rows are 32-byte aligned: the two sectors shared with the kin part / the newest slot are then written
                 // whole by the drone's own thread (no partial-sector L2 fills from DRAM); the two old slots it needs
                 // (1 and B-1) arrive through two more, 16-byte-wide TMA boxes on the same mbarrier.
+                if (a.tile_dep) fence_proxy_async_global();     // generic-proxy writes of the tile's previous step -> TMA reads
                 mbar_expect_tx(&tma_bar, (uint32_t)(a.tma_bytes_box + (a.tma_edge ? 2 * a.DPB * 16 : 0)));
                 if (a.tma_edge) {
                     tma_load_2d(smem_raw + a.tma_bytes - 2 * a.tma_edge_bytes, &tm_edge, 16, (int)row0, &tma_bar);
@@ -375,6 +417,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 5] = gtime();    // 5: history tile landed in smem
                 tma_store_2d(&tm_out, 12 + 4 * a.tma_edge, (int)row0, smem_raw);
                 if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 6] = gtime();    // 6: TMA store has read smem
+                if (a.tile_dep) tma_store_wait_all();
             }
         }
     }
@@ -394,7 +437,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool pre_init = a.auto_reset && !a.init_per_env;      // shared initial pose: fetch it now, off the epilogue's critical path
     if (active) {
         load_state(a.p, d, s);
-        if (!ctrl) tg = a.p.target[i];
+        if (!ctrl) tg = a.p.target[a.target_per_env ? d : (int64_t)i];
         if (pre_init) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
         if (i == 0) {                   // per-env bookkeeping: loaded here so its DRAM latency hides behind the physics
             cnt = a.p.counter[e];
@@ -427,8 +470,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         } else {
             const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
             if constexpr (VEC) {
-                float4 v = __ldg(reinterpret_cast<const float4*>(ap));
-                act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+                act[0] = act_pre.x; act[1] = act_pre.y; act[2] = act_pre.z; act[3] = act_pre.w;
             } else {
                 for (int k = 0; k < a.A; ++k) act[k] = __ldg(ap + k);
             }
@@ -652,6 +694,11 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         }
     }
 
+    if (a.kin_t && active && !ctrl) {   // host mirror (gpd_step_mirror): feature-major copy of the kin part, coalesced per feature
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.D + d] = kin[k];
+    }
+
     // ---- stage this drone's observation row in shared memory ----
     if (t < a.DPB) {
         if (ctrl) {                     // CtrlAviary.py:117: obs = state20 rows
@@ -688,7 +735,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     if (!a.pdl_trigger_early) pdl_launch_dependents();   // this CTA has issued all its loads and (physics warps) stores
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 4] = gtime();      // 4: physics thread 0 stored everything
     // ---- Ctrl observation tile: coalesced write of the staged state20 rows (contiguous in global memory) ----
-    if (ctrl || a.auto_reset) __syncthreads();
+    if (ctrl || a.auto_reset || a.tile_dep) __syncthreads();
     if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 7] = gtime();      // 7: block barrier passed
     if (ctrl) {
         const R* st = sm.stage_r();
@@ -716,6 +763,13 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             if (st > 0.f) atomicAdd(&slot->s[5], (double)st);
         }
         atomicAdd(&slot->s[4], (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)blockIdx.x * a.EPB) : rows));
+    }
+    if (a.tile_dep) {
+        if (ctrl) __syncthreads();      // the tile write-out above is part of what the next step of this tile reads
+        // every global write of this CTA happened before the barrier(s) above: publish the tile (release, gpu scope)
+        if (t == 0) red_release_gpu_inc(a.tile_seq + (int64_t)blockIdx.x * 8 + 1);
+        // keep stream order transitive: this grid does not complete before the grids it was allowed to overtake
+        pdl_wait();
     }
 }
 
@@ -1012,6 +1066,37 @@ rollout_pid_kernel(const __grid_constant__ StepArgs<R> a, int n_steps, const R* 
     reinterpret_cast<V4<R>*>(action)[d] = M<R>::make4(act[0], act[1], act[2], act[3]);
     wp_counters[d] = wp;
     if (i == 0) a.p.counter[e] += a.S * n_steps;
+}
+
+
+// ============================================================================================
+// BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675): adj[e][i][j] = 1 on the diagonal and where
+// ||pos_i - pos_j|| < NEIGHBOURHOOD_RADIUS (np.linalg.norm of a float64 3-vector = sqrt of the in-order sum of squares;
+// pos_i - pos_j with i < j as in the reference loop, mirrored), else 0.  Same per-env position tile in shared memory
+// as the downwash snapshot of the step kernel; a CTA owns whole envs, its threads sweep the N x N outputs contiguously.
+// ============================================================================================
+template <typename R>
+__global__ void __launch_bounds__(256)
+adjacency_kernel(const typename Vec4<R>::type* __restrict__ sP, int64_t E, int N, int EPC, R radius, R* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char adj_smem[];
+    V4<R>* pos = reinterpret_cast<V4<R>*>(adj_smem);
+    const int64_t e0 = (int64_t)blockIdx.x * EPC;
+    const int envs = (int)min((int64_t)EPC, E - e0);
+    for (int k = threadIdx.x; k < envs * N; k += blockDim.x) pos[k] = sP[e0 * N + k];
+    __syncthreads();
+    const int NN = N * N;
+    R* o = out + e0 * NN;
+    for (int idx = threadIdx.x; idx < envs * NN; idx += blockDim.x) {
+        const int le = idx / NN, r = idx - le * NN, i = r / N, j = r - i * N;
+        R v = R(1);
+        if (i != j) {
+            const V4<R> a = pos[le * N + min(i, j)], b = pos[le * N + max(i, j)];
+            const R dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+            v = M<R>::sqrt(dx * dx + dy * dy + dz * dz) < radius ? R(1) : R(0);
+        }
+        o[idx] = v;
+    }
 }
 
 }  // namespace gpd

@@ -1,19 +1,39 @@
 // gpd_launch.inl — launchers, compiled once per precision with GPD_REAL defined (gpd_f32.cu / gpd_f64.cu).
+#include <atomic>
+#include <mutex>
+
 #include "gpd_kernels.cuh"
 
 namespace gpd {
 
 using Real = GPD_REAL;
 
-// The opt-in dynamic shared-memory limit of a step-kernel variant only ever grows (handles of different block sizes share it).
+// The opt-in dynamic shared-memory limit of a kernel is a per-device (per-context) attribute that only ever grows here
+// (handles of different block sizes share it).  Tracked per device ordinal; the slow path is serialised.
+struct SmemLimit {
+    std::atomic<size_t> cur[GPD_MAX_DEVICES];
+    std::mutex mu;
+    SmemLimit() { for (auto& c : cur) c.store(48 * 1024); }
+    template <typename F> cudaError_t ensure(size_t need, F kernel)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= GPD_MAX_DEVICES) return cudaErrorInvalidDevice;
+        if (need <= cur[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        std::lock_guard<std::mutex> lock(mu);
+        if (need <= cur[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        if (e == cudaSuccess) cur[dev].store(need, std::memory_order_release);
+        return e;
+    }
+};
+
 template <int KIND, bool MULTI, bool VEC>
 static cudaError_t ensure_step_smem(size_t need)
 {
-    static size_t cur = 48 * 1024;
-    if (need <= cur) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<Real, KIND, MULTI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-    if (e == cudaSuccess) cur = need;
-    return e;
+    static SmemLimit lim;
+    return lim.ensure(need, step_kernel<Real, KIND, MULTI, VEC>);
 }
 
 template <int KIND, bool MULTI, bool VEC>
@@ -109,13 +129,9 @@ template <>
 cudaError_t launch_reset<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
 {
     const bool vec = a.A == 4 && a.env_kind != GPD_ENV_CTRL && (a.W % 4 == 0);
-    static size_t smem_set[2] = { 48 * 1024, 48 * 1024 };
-    if (lc.smem > smem_set[vec]) {
-        cudaError_t e = vec ? cudaFuncSetAttribute(reset_kernel<Real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem)
-                            : cudaFuncSetAttribute(reset_kernel<Real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
-        if (e != cudaSuccess) return e;
-        smem_set[vec] = lc.smem;
-    }
+    static SmemLimit lim[2];
+    cudaError_t e = vec ? lim[1].ensure(lc.smem, reset_kernel<Real, true>) : lim[0].ensure(lc.smem, reset_kernel<Real, false>);
+    if (e != cudaSuccess) return e;
     if (vec) reset_kernel<Real, true><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
     else reset_kernel<Real, false><<<(unsigned)lc.grid, lc.threads, lc.smem, st>>>(a);
     return cudaGetLastError();
@@ -170,6 +186,17 @@ template <>
 cudaError_t launch_downwash<Real>(const DevDrone<Real>& d, int64_t E, int N, const Real* pos, Real* out, cudaStream_t st)
 {
     downwash_kernel<Real><<<blocks_for(E * N, 128), 128, 0, st>>>(d, E, N, pos, out);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_adjacency<Real>(const StepArgs<Real>& a, Real radius, Real* out, cudaStream_t st)
+{
+    const int N = a.N;
+    const int EPC = N * N >= 256 ? 1 : 256 / (N * N);       // whole envs per CTA
+    const size_t smem = (size_t)EPC * N * sizeof(typename Vec4<Real>::type);
+    const unsigned grid = (unsigned)((a.E + EPC - 1) / EPC);
+    adjacency_kernel<Real><<<grid, 256, smem, st>>>(a.p.sP, a.E, N, EPC, radius, out);
     return cudaGetLastError();
 }
 

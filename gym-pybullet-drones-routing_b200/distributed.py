@@ -37,6 +37,48 @@ def init_process_group_from_env(backend: str | None = None):
     return rank, local, world
 
 
+class NcclStatsComm:
+    """An ``ncclComm_t`` owned by libgpd_b200 for the in-library statistics reduce (``gpd_episode_stats(..., comm, ...)``:
+    one all-gather of 8 doubles + a rank-ordered combine on the device, instead of three ``torch.distributed`` all-reduces).
+    ``torch.distributed`` does not expose its communicator, so rank 0 draws an NCCL unique id and the 128 bytes travel
+    through whatever process group is up (NCCL or gloo); the communicator itself lives in the library.
+
+        comm = NcclStatsComm(device=local_rank)            # after init_process_group
+        job_stats = sim.episode_stats(nccl_comm=comm.handle)
+    """
+
+    def __init__(self, device: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self.lib = _lib.load()
+        self.handle = None
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NcclStatsComm needs an initialised torch.distributed process group to exchange the unique id")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(self.lib.gpd_nccl_unique_id(buf))
+        dev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        uid = bytes(t.cpu().tolist())
+        h = C.c_void_p()
+        _lib.check(self.lib.gpd_nccl_comm_init(uid, rank, world, int(device), C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.gpd_nccl_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def all_reduce_episode_stats(stats, device=None, group=None) -> np.ndarray:
     """Job-wide statistics from per-rank ``gpd_episode_stats`` vectors: sums are added, min/max reduced.
     A rank with no finished episode contributes +inf/-inf to min/max."""

@@ -108,20 +108,29 @@ class BaseAviary:
         self.observation_space = self._observationSpace()
         self._sim = BatchedSim(p, E, N, env_kind=self.ENV_KIND, action_type=self._actionCode(), pyb_freq=pyb_freq,
                                ctrl_freq=ctrl_freq, physics_flags=PHYSICS_FLAGS[physics], precision=precision,
-                               device=device, auto_reset=auto_reset, target_pos=self._targetPositions(),
+                               device=device, auto_reset=auto_reset, target_pos=self._sharedTargets(),
                                episode_len_sec=getattr(self, "EPISODE_LEN_SEC", 8.0),
                                threads_per_block=threads_per_block)
         self._sim.set_init_poses(self.INIT_XYZS, self.INIT_RPYS)
+        tp = self._targetPositions()
+        if tp is not None and np.ndim(tp) == 3:          # per-env initial poses: every env has its own targets
+            self._sim.set_targets(tp)
         self._sim.reset()
         self.RESET_TIME = time.time()
         self._host_out = None
         self._state_cache = None
+        self._numpy_io = False      # the last step took numpy actions: reset() then answers in numpy too
 
     ################################################################################
-    def reset(self, seed: int = None, options: dict = None, as_numpy: bool = False):
-        """Resets every env (BaseAviary.py:220-255; ``seed`` is ignored there too).  Returns ``(obs, info)``."""
+    def reset(self, seed: int = None, options: dict = None, as_numpy: bool | None = None):
+        """Resets every env (BaseAviary.py:220-255; ``seed`` is ignored there too).  Returns ``(obs, info)``.
+        The observation is a numpy array when the env is being stepped with numpy actions (or ``as_numpy=True``), else a
+        CUDA tensor.  Both kinds of step share ONE device observation chain, so the action ring survives the reset
+        (BaseRLAviary.py:153-154) whichever way the env was stepped."""
         self.RESET_TIME = time.time()
         self._state_cache = None
+        if as_numpy is None:
+            as_numpy = self._numpy_io
         if as_numpy:
             return self._sim.reset_host(), self._computeInfo()
         return self._sim.reset(), self._computeInfo()
@@ -141,8 +150,11 @@ class BaseAviary:
         if isinstance(action, np.ndarray):
             if self._host_out is None:
                 self._host_out = self._sim.alloc_host_outputs(pinned=torch.cuda.is_available())
-            obs, rew, term, trunc, _ = self._sim.step_host(action, self._host_out)
-            return obs, rew, term.view(np.bool_), trunc.view(np.bool_), self._computeInfo()
+                self._host_flags = (self._host_out[2].view(np.bool_), self._host_out[3].view(np.bool_))
+            self._numpy_io = True
+            obs, rew = self._sim.step_host(action, self._host_out)[:2]
+            return obs, rew, self._host_flags[0], self._host_flags[1], self._computeInfo()
+        self._numpy_io = False
         obs, rew, term, trunc = self._sim.step(action)
         return obs, rew, term.view(torch.bool), trunc.view(torch.bool), self._computeInfo()
 
@@ -194,9 +206,7 @@ class BaseAviary:
 
     def _getAdjacencyMatrix(self):
         """(E, N, N) adjacency (BaseAviary.py:658-675)."""
-        p = self.pos
-        d = torch.linalg.norm(p[:, :, None, :] - p[:, None, :, :], dim=-1)
-        return (d < self.NEIGHBOURHOOD_RADIUS).to(p.dtype)
+        return self._sim.adjacency(self.NEIGHBOURHOOD_RADIUS)       # gpd_adjacency: per-env position tile in shared memory
 
     def _calculateNextStep(self, current_position, destination, step_size=1):
         """Intermediate waypoint at most ``step_size`` from the current position (BaseAviary.py:1105-1147);
@@ -218,8 +228,7 @@ class BaseAviary:
     def restore(self, ckpt):
         sim = self._sim
         sim.set_state(ckpt["state20"], ckpt["rpy_rates"], ckpt["pid_state"], ckpt["step_counter"])
-        sim.obs_buf[sim._cur].copy_(ckpt["obs"])
-        sim._have_prev = True
+        sim.adopt_obs(ckpt["obs"])          # also marks a host mirror stale: it is rebuilt from this observation
         self._state_cache = None
 
     #### hooks of the subclasses (BaseAviary.py:1018-1101) ############################
@@ -234,6 +243,11 @@ class BaseAviary:
 
     def _targetPositions(self):
         return None
+
+    def _sharedTargets(self):
+        """(N,3) targets for ``gpd_create`` (per-env targets, if any, are uploaded with ``gpd_set_targets``)."""
+        tp = self._targetPositions()
+        return None if tp is None else (tp if np.ndim(tp) == 2 else tp[0])
 
     def _computeInfo(self):
         return {"answer": 42}

@@ -21,6 +21,6 @@ class MultiHoverAviary(BaseRLAviary):
                          ctrl_freq=ctrl_freq, gui=gui, record=record, obs=obs, act=act, **batch_kwargs)
 
     def _targetPositions(self):
-        init = self.INIT_XYZS if self.INIT_XYZS.ndim == 2 else self.INIT_XYZS[0]
-        self.TARGET_POS = init + np.array([[0, 0, 1 / (i + 1)] for i in range(self.NUM_DRONES)])
+        # MultiHoverAviary.py:71 — with per-env initial poses (E,N,3) every env hovers above ITS OWN start pose
+        self.TARGET_POS = self.INIT_XYZS + np.array([[0, 0, 1 / (i + 1)] for i in range(self.NUM_DRONES)])
         return self.TARGET_POS

@@ -8,6 +8,7 @@ ping-pong pair because the RL observation carries the action ring (reference
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -19,6 +20,30 @@ from .utils.enums import DroneModel
 
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class HostMirror:
+    """Feature-major observation log in pinned host memory (``gpd_mirror_alloc``; layout in ``include/gpd.h``).
+
+    ``log[row][col]``: row = observation feature, col = drone.  The observation of the current step is the strided view
+    ``obs(e, n, j) = log[first_row + j][col0 + e*N + n]`` — shape ``(E, N, W)``, strides ``(4N, 4, 4*row_len)`` bytes, the
+    transpose of a dense ``[W][D]`` block.  One mirror may serve several sims (env pools in lockstep) through different
+    ``col0``.  The pinned block is released when the last numpy view of it is gone."""
+
+    def __init__(self, W: int, A: int, row_len: int, slide_steps: int = 128):
+        self.lib = _lib.load()
+        self.W, self.A, self.row_len = int(W), int(A), int(row_len)
+        self.rows = self.W + self.A * max(1, int(slide_steps))
+        base = C.c_void_p()
+        _lib.check(self.lib.gpd_mirror_alloc(self.rows, self.row_len, C.byref(base)))
+        self.base = base
+        self._buf = (C.c_float * (self.rows * self.row_len)).from_address(base.value)
+        weakref.finalize(self._buf, self.lib.gpd_mirror_free, C.c_void_p(base.value))
+
+    def view(self, first_row: int, E: int, N: int, col0: int = 0) -> np.ndarray:
+        return np.ndarray((E, N, self.W), dtype=np.float32, buffer=self._buf,
+                          offset=(int(first_row) * self.row_len + int(col0)) * 4,
+                          strides=(4 * N, 4, 4 * self.row_len))
 
 
 class BatchedSim:
@@ -83,6 +108,9 @@ class BatchedSim:
                                  if self.auto_reset and not self.is_ctrl else None)
         self._cur = 0
         self._have_prev = False
+        self._mirror = None
+        self._mirror_col0 = 0
+        self._row = C.c_int64(0)
         # the step path re-uses these ctypes pointers (the buffers never move): eager stepping is host-bound at 65k envs
         self._p_obs = [_ptr(b) for b in self.obs_buf]
         self._p_out = (_ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), _ptr(self.terminal_kin))
@@ -93,6 +121,14 @@ class BatchedSim:
     # ------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_targets(self, target_pos):
+        """TARGET_POS (HoverAviary.py:51, MultiHoverAviary.py:71): (N,3) shared by every env or (E,N,3) per env."""
+        t = np.ascontiguousarray(np.asarray(target_pos, dtype=np.float64))
+        per_env = t.ndim == 3
+        if t.shape != ((self.E, self.N, 3) if per_env else (self.N, 3)):
+            raise ValueError("target_pos must have shape (N,3) or (E,N,3)")
+        _lib.check(self.lib.gpd_set_targets(self.h, t.ctypes.data_as(C.POINTER(C.c_double)), int(per_env)))
 
     def set_init_poses(self, xyz, rpy):
         """initial_xyzs / initial_rpys (BaseAviary.py:194-207): (N,3) for all envs or (E,N,3) per env."""
@@ -154,39 +190,94 @@ class BatchedSim:
         """Makes ``obs`` (the latest observation written by ``step_into``) the current internal observation."""
         self.obs_buf[self._cur].copy_(obs.reshape(self.obs_buf[self._cur].shape))
         self._have_prev = True
-        _lib.check(self.lib.gpd_note_latest_obs(self.h, self._p_obs[self._cur]))     # `obs` may be released by its owner
+        # `obs` may be released by its owner; a host mirror is rebuilt from the adopted observation at its next use
+        _lib.check(self.lib.gpd_note_latest_obs(self.h, self._p_obs[self._cur]))
 
     # host-buffer path: what a numpy call site (the reference's own step signature) sees
-    def step_host(self, actions: np.ndarray, out=None):
+    def attach_mirror(self, mirror: HostMirror | None = None, col0: int = 0, slide_steps: int = 128):
+        """Binds a host mirror (RL envs): numpy steps then return strided views of its pinned log and the device sends back
+        only what it computed (kin, reward, flags).  ``mirror=None`` allocates a private one."""
+        if self.is_ctrl:
+            raise ValueError("the Ctrl observation has no action ring to mirror")
+        if mirror is None:
+            mirror = HostMirror(self.W, self.A, self.E * self.N, slide_steps)
+        _lib.check(self.lib.gpd_mirror_attach(self.h, mirror.base, mirror.rows, mirror.row_len, int(col0)))
+        self._mirror, self._mirror_col0 = mirror, int(col0)
+        return mirror
+
+    def _host_actions(self, actions):
         adt = self.np_real if self.is_ctrl else np.float32
         a = np.ascontiguousarray(actions, dtype=adt)
         if a.size != self.E * self.N * self.A:
             raise ValueError(f"actions must have {self.E}x{self.N}x{self.A} elements, got {a.shape}")
+        return a
+
+    def step_host_begin(self, actions: np.ndarray, out):
+        """Enqueues one numpy-facing step on the current stream (mirror path) without waiting for it."""
+        a = self._host_actions(actions)
+        _, rew, term, trunc, tkin = out
+        nxt = self._cur ^ 1
+        _lib.check(self.lib.gpd_step_mirror_begin(
+            self.h, C.c_void_p(a.ctypes.data), self._p_obs[self._cur] if self._have_prev else None, self._p_obs[nxt],
+            C.c_void_p(rew.ctypes.data), C.c_void_p(term.ctypes.data), C.c_void_p(trunc.ctypes.data),
+            None if tkin is None else C.c_void_p(tkin.ctypes.data), self._stream()))
+        self._cur, self._have_prev = nxt, True
+        self._pending_actions = a          # the library reads it until the step is complete
+
+    def step_host_end(self) -> int:
+        _lib.check(self.lib.gpd_step_mirror_end(self.h, C.byref(self._row), self._stream()))
+        self._pending_actions = None
+        return self._row.value
+
+    def step_host(self, actions: np.ndarray, out=None):
+        """One BaseAviary.step on numpy arrays.  RL envs: the host-mirror path (``gpd_step_mirror``) on the sim's own device
+        observation chain — the returned observation is a strided view of the pinned log, valid until the next step.
+        Ctrl env: ``gpd_step_host`` (every byte of its observation is device-computed)."""
         if out is None:
             out = self.alloc_host_outputs()
-        obs, rew, term, trunc, tkin = out
-        _lib.check(self.lib.gpd_step_host(self.h, C.c_void_p(a.ctypes.data), C.c_void_p(obs.ctypes.data),
-                                          C.c_void_p(rew.ctypes.data), C.c_void_p(term.ctypes.data),
-                                          C.c_void_p(trunc.ctypes.data),
-                                          None if tkin is None else C.c_void_p(tkin.ctypes.data), self._stream()))
-        return out
+        if self.is_ctrl:
+            a = self._host_actions(actions)
+            obs, rew, term, trunc, tkin = out
+            _lib.check(self.lib.gpd_step_host(self.h, C.c_void_p(a.ctypes.data), C.c_void_p(obs.ctypes.data),
+                                              C.c_void_p(rew.ctypes.data), C.c_void_p(term.ctypes.data),
+                                              C.c_void_p(trunc.ctypes.data), None, self._stream()))
+            return out
+        if self._mirror is None:
+            self.attach_mirror()
+        self.step_host_begin(actions, out)
+        row = self.step_host_end()
+        return (self._mirror.view(row, self.E, self.N, self._mirror_col0),) + tuple(out[1:])
 
     def reset_host(self, mask: np.ndarray | None = None, obs: np.ndarray | None = None):
-        if obs is None:
-            obs = np.empty((self.E, self.N, self.W), dtype=self.np_real if self.is_ctrl else np.float32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        _lib.check(self.lib.gpd_reset_host(self.h, None if m is None else C.c_void_p(m.ctypes.data),
-                                           C.c_void_p(obs.ctypes.data), self._stream()))
-        return obs
+        if self.is_ctrl:
+            if obs is None:
+                obs = np.empty((self.E, self.N, self.W), dtype=self.np_real)
+            _lib.check(self.lib.gpd_reset_host(self.h, None if m is None else C.c_void_p(m.ctypes.data),
+                                               C.c_void_p(obs.ctypes.data), self._stream()))
+            return obs
+        if self._mirror is None:
+            self.attach_mirror()
+        nxt = self._cur ^ 1
+        _lib.check(self.lib.gpd_reset_mirror(self.h, None if m is None else C.c_void_p(m.ctypes.data),
+                                             self._p_obs[self._cur] if self._have_prev else None, self._p_obs[nxt],
+                                             C.byref(self._row), self._stream()))
+        self._cur, self._have_prev = nxt, True
+        view = self._mirror.view(self._row.value, self.E, self.N, self._mirror_col0)
+        if obs is not None:
+            obs[...] = view
+            return obs
+        return view
 
     def alloc_host_outputs(self, pinned: bool = False, terminal_kin: bool | None = None):
-        """Host result arrays (obs, reward, terminated, truncated, terminal_kin|None) carved out of ONE block laid out
-        [obs | reward | terminated | truncated], so gpd_step_host returns everything in a single device-to-host copy.
-        ``terminal_kin`` (12 floats per drone, needed only to rebuild SB3's terminal_observation) is transferred only
-        when asked for (default: never for plain step(), always for the VecEnv adapter)."""
+        """Host result arrays ``(obs|None, reward, terminated, truncated, terminal_kin|None)``.  reward / terminated /
+        truncated are carved out of ONE block laid out like the device staging, so they travel in a single device-to-host
+        copy.  RL envs: ``obs`` is None (the observation is a view of the host mirror).  Ctrl env: a dense ``obs`` array
+        heads the same block.  ``terminal_kin`` (12 floats per drone, needed only to rebuild SB3's terminal_observation)
+        is transferred only when asked for (default: never for plain step(), always for the VecEnv adapter)."""
         odt = np.dtype(self.np_real if self.is_ctrl else np.float32)
         rdt = np.dtype(self.np_real)
-        obs_b = self.E * self.N * self.W * odt.itemsize
+        obs_b = self.E * self.N * self.W * odt.itemsize if self.is_ctrl else 0
         obs_pad = (obs_b + 15) & ~15                      # same padding as gpd_step_host's packed device block
         rew_b = self.E * rdt.itemsize
         total = obs_pad + rew_b + 2 * self.E
@@ -194,7 +285,7 @@ class BatchedSim:
             block = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
         else:
             block = np.empty(total, dtype=np.uint8)
-        obs = block[:obs_b].view(odt).reshape(self.E, self.N, self.W)
+        obs = block[:obs_b].view(odt).reshape(self.E, self.N, self.W) if self.is_ctrl else None
         rew = block[obs_pad:obs_pad + rew_b].view(rdt)
         term = block[obs_pad + rew_b:obs_pad + rew_b + self.E]
         trunc = block[obs_pad + rew_b + self.E:]
@@ -232,10 +323,18 @@ class BatchedSim:
         _lib.check(self.lib.gpd_rollout_pid(self.h, int(n_ctrl_steps), _ptr(waypoints.contiguous()),
                                             int(waypoints.shape[0]), _ptr(wp_counters), _ptr(action), self._stream()))
 
-    def episode_stats(self, clear: bool = False) -> np.ndarray:
+    def episode_stats(self, clear: bool = False, nccl_comm=None) -> np.ndarray:
+        """This sim's episode statistics, or — with an ``ncclComm_t`` from ``distributed.NcclStatsComm`` — the job-wide
+        ones, reduced inside the library (one all-gather)."""
         out = (C.c_double * 8)()
-        _lib.check(self.lib.gpd_episode_stats(self.h, out, int(clear), self._stream()))
+        _lib.check(self.lib.gpd_episode_stats(self.h, out, int(clear), nccl_comm, self._stream()))
         return np.array(list(out))
+
+    def adjacency(self, radius: float) -> torch.Tensor:
+        """(E, N, N) adjacency matrices from the current positions (BaseAviary.py:658-675)."""
+        out = torch.empty((self.E, self.N, self.N), dtype=self.real, device=self.device)
+        _lib.check(self.lib.gpd_adjacency(self.h, float(radius), _ptr(out), self._stream()))
+        return out
 
     def count_nonfinite(self) -> int:
         """Drones whose integrator state holds a NaN/Inf (failure detection; off the step path)."""

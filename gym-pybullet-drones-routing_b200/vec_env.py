@@ -1,4 +1,5 @@
-"""SB3-protocol ``VecEnv`` over one batched aviary (caller side: ``examples/learn.py:53-94``).
+"""SB3-protocol ``VecEnv`` over one batched aviary or several env pools (caller side:
+``examples/learn.py:53-94``).
 
 stable-baselines3 is not installable in the build image, so the adapter is duck-typed: ``num_envs``,
 ``observation_space``/``action_space`` (of ONE env), ``reset() -> obs``, ``step_async/step_wait``, ``step``,
@@ -7,6 +8,12 @@ stable-baselines3 is not installable in the build image, so the adapter is duck-
 ``infos[i]["episode"] = {"r","l","t"}``.  At 65k envs a Python list of dicts per step is the bottleneck, not the
 kernel: ``infos`` is a lazy sequence that builds a dict only for the indices a consumer touches, and
 ``step_tensor`` is the tensor-native entry point for device-side policies.
+
+``num_pools > 1`` splits the envs into equal pools (what ``SubprocVecEnv`` workers are in the reference,
+``examples/learn.py:53-57``), each a batched aviary stepping on its own CUDA stream.  One numpy batch goes in and one
+comes out: the pools share ONE host mirror (``sim.HostMirror``, a pinned feature-major log) through different column
+offsets, so the observation is a single strided view over all pools, and because PCIe is full duplex one pool's
+host-to-device action copy overlaps another pool's device-to-host result copy.
 """
 from __future__ import annotations
 
@@ -15,6 +22,8 @@ from collections.abc import Sequence
 
 import numpy as np
 import torch
+
+from .sim import HostMirror
 
 
 class LazyInfos(Sequence):
@@ -43,11 +52,16 @@ class LazyInfos(Sequence):
 
 
 class GpdVecEnv:
-    def __init__(self, env_cls, num_envs: int, **env_kwargs):
+    def __init__(self, env_cls, num_envs: int, num_pools: int = 1, slide_steps: int = 128, **env_kwargs):
         env_kwargs = dict(env_kwargs)
-        env_kwargs.update(num_envs=num_envs, auto_reset=True)
-        self.env = env_cls(**env_kwargs)
         self.num_envs = int(num_envs)
+        self.num_pools = int(num_pools)
+        if self.num_pools < 1 or self.num_envs % self.num_pools:
+            raise ValueError("num_envs must be a multiple of num_pools")
+        per = self.num_envs // self.num_pools
+        env_kwargs.update(num_envs=per, auto_reset=True)
+        self.envs = [env_cls(**env_kwargs) for _ in range(self.num_pools)]
+        self.env = self.envs[0]
         self.observation_space = self.env.observation_space
         self.action_space = self.env.action_space
         self.render_mode = None
@@ -56,10 +70,63 @@ class GpdVecEnv:
         self._ep_r = np.zeros(self.num_envs)
         self._ep_l = np.zeros(self.num_envs, dtype=np.int64)
         self.reset_infos = [{} for _ in range(min(self.num_envs, 1))]
+        sim0 = self.env._sim
+        self._per, self._N = per, sim0.N
+        self._device = sim0.device
+        self._streams = [None] + [torch.cuda.Stream(device=self._device) for _ in range(self.num_pools - 1)]
+        self._mirror = None
+        self._outs = None
+        self._slide_steps = int(slide_steps)
+
+    # ---- host buffers: ONE mirror and ONE set of result arrays for all pools --------------
+    def _ensure_host(self):
+        if self._outs is not None:
+            return
+        sim0 = self.env._sim
+        E, N, P = self.num_envs, self._N, self.num_pools
+        if not sim0.is_ctrl:
+            self._mirror = HostMirror(sim0.W, sim0.A, E * N, slide_steps=self._slide_steps)
+            for j, env in enumerate(self.envs):
+                env._sim.attach_mirror(self._mirror, col0=j * self._per * N)
+        rdt = np.dtype(sim0.np_real)
+        pin = torch.cuda.is_available()
+
+        def host(shape, dt):
+            n = int(np.prod(shape)) * np.dtype(dt).itemsize
+            b = torch.empty(n, dtype=torch.uint8).pin_memory().numpy() if pin else np.empty(n, np.uint8)
+            return b.view(dt).reshape(shape)
+        # per pool [reward | terminated | truncated] packed like the device staging: one device-to-host copy per pool
+        blk = self._per * (rdt.itemsize + 2)
+        raw = host((P, blk), np.uint8)
+        self._rew_p = [raw[j, :self._per * rdt.itemsize].view(rdt) for j in range(P)]
+        self._term_p = [raw[j, self._per * rdt.itemsize:self._per * (rdt.itemsize + 1)] for j in range(P)]
+        self._trunc_p = [raw[j, self._per * (rdt.itemsize + 1):] for j in range(P)]
+        self._tkin = host((E, N, 12), np.float32) if not sim0.is_ctrl else None
+        self._rew = np.empty(E, rdt)
+        self._term = np.empty(E, np.bool_)
+        self._trunc = np.empty(E, np.bool_)
+        self._obs_ctrl = host((E, N, sim0.W), rdt) if sim0.is_ctrl else None
+        self._outs = [(None if self._obs_ctrl is None else self._obs_ctrl[j * self._per:(j + 1) * self._per],
+                       self._rew_p[j], self._term_p[j], self._trunc_p[j],
+                       None if self._tkin is None else self._tkin[j * self._per:(j + 1) * self._per]) for j in range(P)]
+
+    def _on(self, j):
+        st = self._streams[j]
+        return torch.cuda.stream(st) if st is not None else torch.cuda.stream(torch.cuda.current_stream(self._device))
 
     # ---- SB3 VecEnv protocol ----------------------------------------------------------
     def reset(self):
-        obs, _ = self.env.reset(as_numpy=True)
+        self._ensure_host()
+        obs = None
+        for j, env in enumerate(self.envs):
+            with self._on(j):
+                o, _ = env.reset(as_numpy=True)
+            if self._obs_ctrl is not None:
+                self._obs_ctrl[j * self._per:(j + 1) * self._per] = o
+        if self._mirror is not None:
+            obs = self._mirror.view(self.env._sim._row.value, self.num_envs, self._N, 0)
+        else:
+            obs = self._obs_ctrl
         self._ep_r[:] = 0
         self._ep_l[:] = 0
         return obs
@@ -68,16 +135,34 @@ class GpdVecEnv:
         self._actions = np.asarray(actions)
 
     def step_wait(self):
-        sim = self.env._sim
-        if self.env._host_out is None:
-            self.env._host_out = sim.alloc_host_outputs(pinned=torch.cuda.is_available(), terminal_kin=True)
-        obs, rew, term, trunc, tkin = sim.step_host(self._actions, self.env._host_out)
-        self.env._state_cache = None
-        term_b, trunc_b = term.view(np.bool_), trunc.view(np.bool_)
+        self._ensure_host()
+        P, per = self.num_pools, self._per
+        acts = self._actions.reshape(self.num_envs, -1)
+        if self._mirror is not None:
+            for j, env in enumerate(self.envs):            # enqueue every pool, then complete them in order
+                with self._on(j):
+                    env._sim.step_host_begin(acts[j * per:(j + 1) * per], self._outs[j])
+                env._state_cache = None
+            for j, env in enumerate(self.envs):
+                with self._on(j):
+                    row = env._sim.step_host_end()
+            obs = self._mirror.view(row, self.num_envs, self._N, 0)
+        else:
+            for j, env in enumerate(self.envs):
+                with self._on(j):
+                    env._sim.step_host(acts[j * per:(j + 1) * per], self._outs[j])
+                env._state_cache = None
+            obs = self._obs_ctrl
+        for j in range(P):
+            sl = slice(j * per, (j + 1) * per)
+            self._rew[sl] = self._rew_p[j]
+            self._term[sl] = self._term_p[j].view(np.bool_)
+            self._trunc[sl] = self._trunc_p[j].view(np.bool_)
+        rew, term_b, trunc_b = self._rew, self._term, self._trunc
         dones = term_b | trunc_b
         self._ep_r += rew
         self._ep_l += 1
-        infos = LazyInfos(self.num_envs, dones.copy(), term_b.copy(), trunc_b.copy(), obs, tkin,
+        infos = LazyInfos(self.num_envs, dones.copy(), term_b.copy(), trunc_b.copy(), obs, self._tkin,
                           self._ep_r.copy(), self._ep_l.copy(), self._t0)
         self._ep_r[dones] = 0
         self._ep_l[dones] = 0
@@ -89,13 +174,31 @@ class GpdVecEnv:
 
     def step_tensor(self, actions: torch.Tensor):
         """Device-side step: CUDA tensors in and out, no host copies, no info dicts.
-        Returns (obs, reward, terminated, truncated); ``self.env._sim.terminal_kin`` holds the terminal rows."""
-        self.env._state_cache = None
-        obs, rew, term, trunc = self.env._sim.step(actions)
+        Returns (obs, reward, terminated, truncated); ``self.env._sim.terminal_kin`` holds the terminal rows.
+        With several pools the per-pool outputs are concatenated (one device copy each)."""
+        if self.num_pools == 1:
+            self.env._state_cache = None
+            obs, rew, term, trunc = self.env._sim.step(actions)
+            return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
+        per = self._per
+        cur = torch.cuda.current_stream(self._device)
+        outs = []
+        for j, env in enumerate(self.envs):
+            env._state_cache = None
+            st = self._streams[j]
+            if st is not None:
+                st.wait_stream(cur)
+            with self._on(j):
+                outs.append(env._sim.step(actions[j * per:(j + 1) * per]))
+        for st in self._streams:
+            if st is not None:
+                cur.wait_stream(st)
+        obs, rew, term, trunc = (torch.cat([o[k] for o in outs]) for k in range(4))
         return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
 
     def close(self):
-        self.env.close()
+        for e in self.envs:
+            e.close()
 
     def seed(self, seed=None):
         return [None] * self.num_envs      # the reference ignores seeds too (BaseAviary.py:243)
@@ -105,7 +208,8 @@ class GpdVecEnv:
         return [v for _ in self._idx(indices)]
 
     def set_attr(self, attr_name, value, indices=None):
-        setattr(self.env, attr_name, value)
+        for e in self.envs:
+            setattr(e, attr_name, value)
 
     def env_method(self, method_name, *args, indices=None, **kwargs):
         r = getattr(self.env, method_name)(*args, **kwargs)
@@ -115,7 +219,16 @@ class GpdVecEnv:
         return [False for _ in self._idx(indices)]
 
     def episode_stats(self, clear=False):
-        return self.env._sim.episode_stats(clear)
+        s = np.zeros(8)
+        any_ep = False
+        for e in self.envs:
+            v = e._sim.episode_stats(clear)
+            s[[0, 1, 2, 3, 6, 7]] += v[[0, 1, 2, 3, 6, 7]]
+            if v[0] > 0:
+                s[4] = v[4] if not any_ep else min(s[4], v[4])
+                s[5] = v[5] if not any_ep else max(s[5], v[5])
+                any_ep = True
+        return s
 
     def _idx(self, indices):
         if indices is None:

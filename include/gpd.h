@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GPD_VERSION 100            /* 0.1.0 */
+#define GPD_VERSION 200            /* 0.2.0 */
 #define GPD_MAX_DRONES_PER_ENV 256 /* one thread block owns whole envs */
 
 typedef enum gpd_status {
@@ -125,6 +125,11 @@ int gpd_substeps(const gpd_sim* sim);      /* PYB_STEPS_PER_CTRL, BaseAviary.py:
  * (every env identical, as in the reference) or [E][N][3] when per_env == 1. Takes effect at the next reset. */
 int gpd_set_init_poses(gpd_sim* sim, const double* xyz, const double* rpy, int per_env);
 
+/* TARGET_POS after construction (HoverAviary.py:51; MultiHoverAviary.py:71 TARGET_POS = INIT_XYZS + [0,0,1/(i+1)]).
+ * Host float64 [N][3] (per_env == 0, every env shares the targets — the reference) or [E][N][3] (per_env == 1: envs that
+ * start from their own poses are rewarded and terminated against their own targets). Drains the device. */
+int gpd_set_targets(gpd_sim* sim, const double* target_pos, int per_env);
+
 /* BaseAviary.reset (BaseAviary.py:220-255, _housekeeping :451-477) for the envs with env_mask[e] != 0
  * (dev uint8 [E]; NULL = all). The action ring and the in-env controllers are NOT reset
  * (BaseRLAviary.py:153-154,76). Writes the observation of every env into obs_out; the ring part of it is
@@ -156,6 +161,47 @@ int gpd_step(gpd_sim* sim, const void* actions, const void* obs_prev, void* obs_
 int gpd_step_host(gpd_sim* sim, const void* actions, void* obs_out, void* reward,
                   uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream);
 int gpd_reset_host(gpd_sim* sim, const uint8_t* env_mask, void* obs_out, void* stream);
+
+/*
+ * Host mirror of the RL observation: the numpy-facing step without the echo.
+ *
+ * 83 % of an RL observation row is the action ring (BaseRLAviary.py:187,307-319) — values the HOST sent. gpd_step_host
+ * ships them back over PCIe every step (19.3 MB per 65,536-env HoverAviary step); gpd_step_mirror ships only what the
+ * device computed (12 kinematic floats per drone, reward, terminated, truncated: 54 B per env, 3.5 MB) and keeps the host
+ * observation in a FEATURE-MAJOR log in pinned host memory, log[row][col] (row = observation feature, col = drone):
+ *     obs(e, n, j) of the current step = log[(first_row + j) * row_len + col0 + e*N + n],   j = 0 .. W-1
+ * i.e. a strided view of shape (E, N, W) with element strides (N, 1, row_len) — the transpose of a dense [W][D] block.
+ * A step slides the window by A rows: the 12 kin rows land (one contiguous device-to-host copy) on the rows the oldest ring
+ * entry and the old kin rows occupied, the newest action is written by the host itself (transposed from `actions` while the
+ * device works) behind the window. When the window reaches the end of the log it is rebuilt at row 0 from the device
+ * observation (one W-row copy every (rows - W) / A steps); the same rebuild re-synchronises a mirror that went stale because
+ * gpd_step / gpd_reset advanced the device chain without it. A view returned by step t stays intact until step t+1 begins.
+ *
+ *   gpd_mirror_alloc   pinned (cudaHostAlloc), zero-filled log of rows x row_len floats; gpd_mirror_free releases it
+ *   gpd_mirror_attach  binds a log to a handle: rows >= W + A, row_len >= col0 + E*N. Several handles (env pools stepping
+ *                      in lockstep) may share one log through different col0: their windows stay aligned and ONE strided
+ *                      view covers all pools. RL envs only (the Ctrl observation has no ring: gpd_step_host).
+ *   gpd_step_mirror    actions: host [E][N][A] float32 (pinned or pageable). d_obs_prev / d_obs_out: the DEVICE observation
+ *                      chain exactly as in gpd_step (caller-owned, so tensor-path and numpy-path steps share one chain);
+ *                      d_obs_out == NULL selects the handle's internal ping-pong. reward (Real) / terminated / truncated /
+ *                      terminal_kin: host arrays, any may be NULL. *first_row receives the window's first row after the step.
+ *                      Synchronises `stream`. _begin enqueues the device work and returns; _end writes the newest action into
+ *                      the log (`actions` must stay valid until then), synchronises and publishes the window — several pools
+ *                      on their own streams overlap one pool's H2D with another's D2H.
+ *   gpd_reset_mirror   BaseAviary.reset for env_mask (HOST uint8 [E] or NULL = all): the ring survives (BaseRLAviary.py:153-154),
+ *                      the window does not move, its 12 kin rows are refreshed.
+ */
+int gpd_mirror_alloc(int64_t rows, int64_t row_len, float** log_out);
+int gpd_mirror_free(float* log);
+int gpd_mirror_attach(gpd_sim* sim, float* log, int64_t rows, int64_t row_len, int64_t col0);
+int64_t gpd_mirror_row(const gpd_sim* sim);
+int gpd_step_mirror(gpd_sim* sim, const void* actions, const void* d_obs_prev, void* d_obs_out, void* reward,
+                    uint8_t* terminated, uint8_t* truncated, void* terminal_kin, int64_t* first_row, void* stream);
+int gpd_step_mirror_begin(gpd_sim* sim, const void* actions, const void* d_obs_prev, void* d_obs_out, void* reward,
+                          uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream);
+int gpd_step_mirror_end(gpd_sim* sim, int64_t* first_row, void* stream);
+int gpd_reset_mirror(gpd_sim* sim, const uint8_t* env_mask, const void* d_obs_prev, void* d_obs_out, int64_t* first_row,
+                     void* stream);
 
 /* BaseAviary._getDroneStateVector (BaseAviary.py:541-561) for every drone + the hidden integrator state.
  *   state20 dev [E][N][20] Real: pos3 quat4 rpy3 vel3 ang_v3 last_clipped_action4
@@ -217,9 +263,23 @@ int gpd_count_nonfinite(gpd_sim* sim, long long* out_host, void* stream);
 /* Episode statistics kept on the device when auto_reset is on (what SB3's Monitor reports in the
  * single-process reference, examples/learn.py:53-57,142-146). out (host) = { episodes, sum_return, sum_length,
  * sum_return_sq, min_return, max_return, env_steps, terminated_episodes }. Synchronises `stream`.
- * clear != 0 zeroes the accumulators afterwards. Sum the first four and the last two across ranks
- * (and min/max) with an all-reduce to get job-wide statistics. */
-int gpd_episode_stats(gpd_sim* sim, double out[8], int clear, void* stream);
+ * clear != 0 zeroes the accumulators afterwards.
+ * nccl_comm: an ncclComm_t (as void*) or NULL. NULL = this handle's statistics. With a communicator the result is
+ * JOB-WIDE on every rank: one ncclAllGather of the 8 doubles + a rank-ordered combine on the device (sums added, min/max
+ * over the ranks that finished an episode) — the only collective of the whole design, off the step path. libnccl.so.2 is
+ * bound at run time (dlopen; the copy already loaded in the process is reused), never linked. */
+int gpd_episode_stats(gpd_sim* sim, double out[8], int clear, void* nccl_comm, void* stream);
+
+/* Communicator plumbing for callers without one (the Python host code: torch.distributed does not expose its ncclComm_t):
+ * rank 0 calls gpd_nccl_unique_id and broadcasts the 128 bytes by any means; every rank then calls gpd_nccl_comm_init. */
+#define GPD_NCCL_UNIQUE_ID_BYTES 128
+int gpd_nccl_unique_id(char id_out[GPD_NCCL_UNIQUE_ID_BYTES]);
+int gpd_nccl_comm_init(const char id[GPD_NCCL_UNIQUE_ID_BYTES], int rank, int world_size, int device, void** comm_out);
+int gpd_nccl_comm_destroy(void* comm);
+
+/* BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675) of every env from the current positions:
+ * out dev [E][N][N] Real, 1 on the diagonal and where ||pos_i - pos_j|| < neighbourhood_radius, else 0. */
+int gpd_adjacency(gpd_sim* sim, double neighbourhood_radius, void* out, void* stream);
 
 #ifdef __cplusplus
 }

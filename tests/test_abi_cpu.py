@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in include/gpd.h but not exported"
     assert sorted(_lib.SYMBOLS) == declared
     L.gpd_version.restype = C.c_int
-    assert L.gpd_version() == 100
+    assert L.gpd_version() == 200
 
 
 def test_struct_layouts_match_header_sizes():

@@ -19,7 +19,10 @@ def test_reference_arm_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "drone-substeps/sec" and d["steps"] == 3
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["gpu_launches"] == 0
-    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    staged = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "gym_pybullet_drones"))
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")     # the reference's own Python when it is staged
+    assert set(d["config"]) >= {"workload", "envs_per_gpu", "substeps_per_step", "parallelism"}
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
 
@@ -29,3 +32,11 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
                           "--warmup", "1", "--envs", "1024"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_port_kind():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-kind", "port", "--steps", "3",
+                          "--warmup", "1", "--envs", "2048"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip().startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 1e6
