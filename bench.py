@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--launch", default="auto", choices=["auto", "direct", "single", "cycles"])
     ap.add_argument("--no-extra", action="store_true", help="skip the informational measurements and other_configs")
     ap.add_argument("--no-others", action="store_true", help="skip other_configs (BASELINE configs[2..4])")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "python", "port"],
@@ -455,36 +456,46 @@ def b200_arm(a):
         run_steps(period)
     torch.cuda.synchronize()
     K = max(1, a.steps)
-    # EXACTLY K steps per timed window.  K <= 1024: each window is ONE graph of K kernel nodes (no tail graph, nothing between
-    # the events but the graph).  The observation ping-pong and the set rotation repeat every `period` steps, so
-    # m = period / gcd(K, period) such graphs are captured back to back and replayed round-robin: every replay continues the
-    # simulation exactly where the previous one stopped.  Longer runs: `reps` replays of the period graph + a tail graph inside
-    # the window (host gaps vanish in a > 10 ms window) and, outside it, the complement that completes the tail's cycle.
+    # EXACTLY K steps per timed window.  Three launch modes (--launch auto picks by K):
+    #   direct  K <= 256: K plain stream launches enqueued while the device sleeps (Timer.window), so none of the host launch
+    #           cost and no graph-launch latency (~8 us per graph, measured) falls between the events; consecutive step kernels
+    #           overlap through programmatic dependent launch exactly as they do in a rollout loop
+    #   single  K <= 1024: ONE graph of K kernel nodes.  The observation ping-pong and the set rotation repeat every `period`
+    #           steps, so m = period / gcd(K, period) such graphs are captured back to back and replayed round-robin: every
+    #           replay continues the simulation exactly where the previous one stopped
+    #   cycles  longer runs: `reps` replays of a 128-step graph + a tail graph inside the window and, outside it, the complement
+    #           that completes the tail's cycle
     from math import gcd
-    single = K <= 1024
-    m = period // gcd(K, period) if single else 1
-    reps, tail = (0, 0) if single else divmod(K, period)
+    mode = a.launch
+    if mode == "auto":
+        mode = "direct" if K <= 256 else ("single" if K <= 1024 else "cycles")
+    if a.no_graph:
+        mode = "direct"
+    gper = period * 8
+    m = period // gcd(K, period)
+    reps, tail = divmod(K, gper) if mode == "cycles" else (0, 0)
     graphs = None
     graph_error = None
-    if not a.no_graph:
+    if mode != "direct":
         try:
-            if single:
+            if mode == "single":
                 graphs = [graph_of(torch, (lambda i=i: run_steps(K, k0=i * K))) for i in range(m)]
             else:
-                graphs = {"main": graph_of(torch, lambda: run_steps(period)),
+                graphs = {"main": graph_of(torch, lambda: run_steps(gper)),
                           "tail": graph_of(torch, lambda: run_steps(tail)) if tail else None,
-                          "comp": graph_of(torch, lambda: run_steps(period - tail, k0=tail)) if tail else None}
+                          "comp": graph_of(torch, lambda: run_steps(gper - tail, k0=tail)) if tail else None}
         except Exception as ex:          # never lose the measurement to a capture problem: fall back to direct launches
             graphs = None
+            mode = "direct"
             graph_error = repr(ex)[:200]
             torch.cuda.synchronize()
-    nxt = [0]           # which of the m graphs (or, without graphs, which step index) comes next
+    nxt = [0]           # which of the m units (graphs, or K-step groups of direct launches) comes next
 
     def timed_unit():
-        if graphs is None:
+        if mode == "direct":
             run_steps(K, k0=nxt[0] * K)
-            nxt[0] = (nxt[0] + 1) % (period // gcd(K, period))
-        elif single:
+            nxt[0] = (nxt[0] + 1) % m
+        elif mode == "single":
             graphs[nxt[0]].replay()
             nxt[0] = (nxt[0] + 1) % m
         else:
@@ -494,7 +505,7 @@ def b200_arm(a):
                 graphs["tail"].replay()
 
     def after_unit():       # untimed: bring the rotation back to a cycle boundary
-        if graphs is not None and not single and tail:
+        if mode == "cycles" and tail:
             graphs["comp"].replay()
 
     def finish_cycle():
@@ -514,7 +525,8 @@ def b200_arm(a):
     est_ms = K * 0.012
     trials = a.trials or (5 if est_ms < 50 else 1)
     windows, per_rank_all = [], []
-    sleep_cycles = 400_000 + 60 * min(K, 4096)
+    # long enough for the host to enqueue the whole window behind it (direct mode: ~10 us of host time per launch)
+    sleep_cycles = 400_000 + (40_000 * K if mode == "direct" else 60 * min(K, 4096))
     for _ in range(trials):
         ms_local = timer.window(timed_unit, sleep_cycles)
         after_unit()
@@ -531,7 +543,7 @@ def b200_arm(a):
 
     # ---- informational: the same job with the env sets as async pools on their own streams (never the headline) ----
     async_info = l2_info = None
-    if nstreams == 1 and graphs is not None and nsets >= 2 and not a.no_extra:
+    if nstreams == 1 and not a.no_graph and nsets >= 2 and not a.no_extra:
         try:
             ns2 = min(8, nsets)
             pool2 = [torch.cuda.Stream(device=dev) for _ in range(ns2 - 1)]
@@ -669,12 +681,13 @@ def b200_arm(a):
                     cpu, _ = port_baseline(a, seconds=a.cpu_seconds)
             except Exception as ex:
                 cpu = {"error": repr(ex)[:300]}
-        if graphs is None:
-            launch = "direct launches" + (f" (graph capture failed: {graph_error})" if graph_error else "")
-        elif single:
+        if mode == "direct":
+            launch = (f"{K} direct stream launches per timed window, enqueued behind a device-side sleep"
+                      + (f" (graph capture failed: {graph_error})" if graph_error else ""))
+        elif mode == "single":
             launch = f"ONE CUDA graph of {K} step kernels per timed window ({m} such graphs replayed round-robin)"
         else:
-            launch = "CUDA graph of %d step kernels x %d replays + %d-step tail graph" % (period, reps, tail)
+            launch = "CUDA graph of %d step kernels x %d replays + %d-step tail graph" % (gper, reps, tail)
         line = {
             "metric": METRIC, "value": value, "unit": "drone-substeps/s", "n_gpus": world, "steps": K, "warmup": wu,
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

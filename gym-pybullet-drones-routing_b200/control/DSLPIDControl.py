@@ -31,6 +31,15 @@ class DSLPIDControl(BaseControl):
         self.state = None
         self.reset()
 
+    _PARAM_NAMES = frozenset(("P_COEFF_FOR", "I_COEFF_FOR", "D_COEFF_FOR", "P_COEFF_TOR", "I_COEFF_TOR", "D_COEFF_TOR",
+                              "PWM2RPM_SCALE", "PWM2RPM_CONST", "MIN_PWM", "MAX_PWM", "MIXER_MATRIX", "GRAVITY", "KF"))
+
+    def __setattr__(self, name, value):
+        # the C parameter block is rebuilt only after a gain / mixer attribute was assigned (setPIDCoefficients or directly)
+        if name in DSLPIDControl._PARAM_NAMES:
+            object.__setattr__(self, "_pc", None)
+        object.__setattr__(self, name, value)
+
     def reset(self):
         """DSLPIDControl.py:65-78: integral errors and last rpy to zero."""
         super().reset()
@@ -66,10 +75,12 @@ class DSLPIDControl(BaseControl):
         n = self.num
         cp, cq, cv, tp = self._t(cur_pos, 3), self._t(cur_quat, 4), self._t(cur_vel, 3), self._t(target_pos, 3)
         tr, tv, trr = self._t(target_rpy, 3), self._t(target_vel, 3), self._t(target_rpy_rates, 3)
-        rpm = torch.empty((n, 4), dtype=self.real, device=self.device)
-        pos_e = torch.empty((n, 3), dtype=self.real, device=self.device)
-        yaw_e = torch.empty((n,), dtype=self.real, device=self.device)
-        pc = _lib.pid_params_c(self._params())
+        out = torch.empty((8, n), dtype=self.real, device=self.device)      # one block: fresh results every call, like the reference
+        rpm, pos_e, yaw_e = out[0:4].view(n, 4), out[4:7].view(n, 3), out[7]
+        pc = getattr(self, "_pc", None)
+        if pc is None:
+            pc = _lib.pid_params_c(self._params())
+            object.__setattr__(self, "_pc", pc)
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self._lib.gpd_pid_compute(self.device_index, _lib.GPD_F64 if self.precision == "f64" else _lib.GPD_F32,

@@ -66,6 +66,7 @@ static int fail(int code, const char* fmt, ...)
 // pinned host memory, log[row][col]: row = observation feature, col = drone.  The window of step t is rows [row, row + W):
 // 12 kin rows then the A*B ring rows, oldest -> newest.  A step slides the window by A rows: the device sends only what it
 // computed (12 kin rows, reward, flags); the newest action is written by the host from its own copy; nothing is echoed.
+enum { GPD_MIRROR_MAX_CHUNKS = 8 };
 struct Mirror {
     float* log = nullptr;
     int64_t rows = 0, ld = 0, col0 = 0;
@@ -75,6 +76,10 @@ struct Mirror {
     const void* synced_obs = nullptr;
     float* d_kin_t = nullptr;       // device [12][D]
     float* d_full_t = nullptr;      // device [W][D], refresh scratch (lazy)
+    int chunks = 1;                 // a step is issued as `chunks` launches over CTA sub-ranges, each with its own copies
+    cudaStream_t cs[GPD_MIRROR_MAX_CHUNKS] = {};   // one stream per chunk: chunk c's H2D overlaps chunk c-1's kernel and D2H
+    cudaEvent_t ce[GPD_MIRROR_MAX_CHUNKS] = {};
+    cudaEvent_t ev_fork = nullptr;
     bool pending = false;           // a begin without its end
     const void* pending_obs = nullptr;
     const float* pending_actions = nullptr;
@@ -89,6 +94,10 @@ struct gpd_sim {
     LaunchCfg lc;
     int dpb = 0;
     int copy_threads = 0;
+    int tile_dep = 1;                 // per-CTA step sequencing (decided in gpd_create from the number of waves)
+    bool bulk_ok = false;             // single-drone RL env with 4-wide actions: the bulk-copy data path (gpd_step_bulk.cuh)
+    LaunchCfg lc_bulk{};
+    int64_t d_pad = 0;                // per-env scalar arrays are allocated for whole tiles (grid * DPB entries)
     const void* last_obs = nullptr;   // the observation buffer most recently written by gpd_step / gpd_reset (device)
     uint64_t obs_seq = 0;             // bumped whenever the device observation chain advances (or is replaced by the caller)
     std::vector<void*> allocs;
@@ -309,7 +318,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     if ((rc = dev_alloc(s, &sP, (size_t)s->D))) return rc;
     if ((rc = dev_alloc(s, &sQ, (size_t)s->D))) return rc;
     if ((rc = dev_alloc(s, &sV, (size_t)s->D))) return rc;
-    if ((rc = dev_alloc(s, &wz, (size_t)s->D))) return rc;
+    if ((rc = dev_alloc(s, &wz, (size_t)s->d_pad))) return rc;       // whole tiles: the bulk path copies T entries per CTA
     if ((rc = dev_alloc(s, &av, (size_t)s->D))) return rc;
     if ((rc = dev_alloc(s, &rp, (size_t)s->D))) return rc;
     a.p.sP = sP; a.p.sQ = sQ; a.p.sV = sV; a.p.sWz = wz; a.p.aux_av = av; a.p.aux_rpm = rp;
@@ -322,11 +331,11 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     (void)pidfam;
     a.p.pid = pid;
     int32_t* cnt;
-    if ((rc = dev_alloc(s, &cnt, (size_t)c.num_envs))) return rc;
+    if ((rc = dev_alloc(s, &cnt, (size_t)(s->d_pad > c.num_envs ? s->d_pad : c.num_envs)))) return rc;
     a.p.counter = cnt;
     if (c.auto_reset) {
         float* er; StatSlot* slots;
-        if ((rc = dev_alloc(s, &er, (size_t)c.num_envs))) return rc;
+        if ((rc = dev_alloc(s, &er, (size_t)(s->d_pad > c.num_envs ? s->d_pad : c.num_envs)))) return rc;
         if ((rc = dev_alloc(s, &slots, (size_t)s->lc.grid))) return rc;
         std::vector<StatSlot> init((size_t)s->lc.grid);
         for (auto& q : init) { for (double& v : q.s) v = 0.0; q.mn = 0x7fffffff; q.mx = (int32_t)0x80000000; }
@@ -338,8 +347,7 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
         uint32_t* seq = nullptr;
         if ((rc = dev_alloc(s, &seq, (size_t)s->lc.grid * 8))) return rc;
         a.tile_seq = seq;
-        const char* ev = getenv("GPD_TILE_DEP");
-        a.tile_dep = ev ? (atoi(ev) ? 1 : 0) : 1;
+        a.tile_dep = s->tile_dep;
     }
     a.DPB = s->dpb;
     a.copy_threads = s->copy_threads;
@@ -520,15 +528,44 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     s->tma_bytes = L.tma_bytes;
     s->lc.smem = L.smem;
     (void)EPB;
+    s->d_pad = s->lc.grid * (int64_t)DPB;
+    {   // bulk-copy data path: same tiles (DPB envs per CTA), T threads, everything staged in shared memory
+        const size_t rs = f64 ? 8 : 4;
+        const size_t bsm = (size_t)DPB * s->W * 4 + 3 * (size_t)DPB * 4 * rs + (size_t)DPB * 16 + 2 * (size_t)DPB * rs +
+                           2 * (size_t)DPB * 4 + 2 * (size_t)DPB + 8 * 32;
+        const char* ev = getenv("GPD_BULK");
+        s->bulk_ok = !(ev && atoi(ev) == 0) && !ctrl && N == 1 && A == 4 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 &&
+                     bsm <= (size_t)smem_optin &&
+                     (cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_VEL);
+        s->lc_bulk.threads = DPB; s->lc_bulk.grid = L.grid; s->lc_bulk.smem = bsm; s->lc_bulk.pdl = 0;
+    }
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
         // parameter fetch overlap the previous kernel's tail); with a full wave the early-resident CTAs all issue their
         // loads at the same instant after the wait and the burst costs more than the overlap gains
-        // With per-CTA step sequencing (GPD_TILE_DEP, the default) there is no whole-grid wait and every step kernel is
-        // launched programmatically: consecutive steps overlap across the kernel boundary at every grid size.
-        const char* ev = getenv("GPD_PDL");
+        // Per-CTA step sequencing (no whole-grid wait; every step kernel launched programmatically, so consecutive steps
+        // overlap across the kernel boundary) pays one L2 round trip at each end of a CTA's life.  Measured (profiles/r02):
+        // 65,536 envs 10.5 -> 9.2 us, FP64 23.9 -> 16.1 us, C3 35.0 -> 27.6 us, 262,144 envs 36.5 -> 35.2 us, but
+        // 1 M envs 130.9 -> 134.1 us and C5 (2 M envs) 439 -> 457 us: with many waves the boundary is a small share of the
+        // launch and the round trips cost more than the overlap gains.  Default: on for launches of at most 4 waves.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        int bps;
+        if (s->bulk_ok)
+            bps = cfg->precision == GPD_F64
+                ? step_bulk_blocks_per_sm<double>(cfg->action_type, cfg->physics_flags, s->lc_bulk.threads, s->lc_bulk.smem)
+                : step_bulk_blocks_per_sm<float>(cfg->action_type, cfg->physics_flags, s->lc_bulk.threads, s->lc_bulk.smem);
+        else
+            bps = cfg->precision == GPD_F64
+                ? step_blocks_per_sm<double>(cfg->action_type, cfg->physics_flags, N, A, s->W, cfg->env_kind, s->lc.threads, s->lc.smem)
+                : step_blocks_per_sm<float>(cfg->action_type, cfg->physics_flags, N, A, s->W, cfg->env_kind, s->lc.threads, s->lc.smem);
+        const double waves = bps > 0 ? (double)s->lc.grid / ((double)bps * sms) : 1e9;
         const char* td = getenv("GPD_TILE_DEP");
-        const bool tile_dep = td ? atoi(td) != 0 : true;
-        s->lc.pdl = ev ? atoi(ev) : ((tile_dep || s->lc.grid <= 296) ? 1 : 0);
+        s->tile_dep = td ? (atoi(td) != 0 ? 1 : 0) : (waves <= 4.0 ? 1 : 0);
+        const char* ev = getenv("GPD_PDL");
+        s->lc.pdl = ev ? atoi(ev) : ((s->tile_dep || s->lc.grid <= 296) ? 1 : 0);
+        s->lc_bulk.pdl = s->lc.pdl;
+        if (getenv("GPD_DEBUG_LAYOUT"))
+            fprintf(stderr, "[gpd] %d CTAs/SM, %.2f waves: tile_dep %d, pdl %d, bulk path %d\n", bps, waves, s->tile_dep, s->lc.pdl, (int)s->bulk_ok);
     }
     if (s->lc.grid > 0x7fffffffLL) { delete s; return fail(GPD_ERR_INVALID, "too many envs for one launch"); }
     int rc = cfg->precision == GPD_F64 ? build_args(s, s->a64) : build_args(s, s->a32);
@@ -552,6 +589,11 @@ void gpd_destroy(gpd_sim* s)
     cudaFree(s->h_tkin); cudaFree(s->h_mask); cudaFree(s->stats_out); cudaFree(s->stats_gather);
     cudaFree(s->init_bufs[0]); cudaFree(s->init_bufs[1]); cudaFree(s->target_buf);
     cudaFree(s->mir.d_kin_t); cudaFree(s->mir.d_full_t);
+    for (int c = 0; c < GPD_MIRROR_MAX_CHUNKS; ++c) {
+        if (s->mir.cs[c]) cudaStreamDestroy(s->mir.cs[c]);
+        if (s->mir.ce[c]) cudaEventDestroy(s->mir.ce[c]);
+    }
+    if (s->mir.ev_fork) cudaEventDestroy(s->mir.ev_fork);
     delete s;
 }
 
@@ -594,7 +636,7 @@ int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* o
 }
 
 static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_out, void* reward, uint8_t* terminated,
-                     uint8_t* truncated, void* terminal_kin, float* kin_t, void* stream)
+                     uint8_t* truncated, void* terminal_kin, float* kin_t, void* stream, int64_t cta0 = 0, int64_t ncta = 0)
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     if (!actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step: actions and obs_out are required");
@@ -608,21 +650,31 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         if (have && s->tma_edge) have = get_tmap(s, obs_prev, true, &te);
     }
     const int use_tma = have ? 1 : 0;
+    // the bulk copies need 16-byte aligned caller buffers (torch allocations are); anything else takes the per-thread path
+    const uintptr_t al = (uintptr_t)actions | (uintptr_t)obs_prev | (uintptr_t)obs_out | (uintptr_t)reward | (uintptr_t)terminated |
+                         (uintptr_t)truncated;
+    const bool bulk = s->bulk_ok && (al & 15) == 0;
+    LaunchCfg lc = bulk ? s->lc_bulk : s->lc;
+    if (ncta > 0) lc.grid = ncta;       // a sub-range of the CTAs (chunked host-mirror step); cta0 shifts the block index
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        a.kin_t = kin_t;
-        CU(launch_step<double>(a, s->lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
+        a.kin_t = kin_t; a.cta0 = (int32_t)cta0;
+        if (bulk) CU(launch_step_bulk<double>(a, lc, st));
+        else CU(launch_step<double>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     } else {
         StepArgs<float> a = s->a32;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        a.kin_t = kin_t;
-        CU(launch_step<float>(a, s->lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
+        a.kin_t = kin_t; a.cta0 = (int32_t)cta0;
+        if (bulk) CU(launch_step_bulk<float>(a, lc, st));
+        else CU(launch_step<float>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     }
-    s->last_obs = obs_out;
-    ++s->obs_seq;
+    if (cta0 + lc.grid >= s->lc.grid) {   // the launch that covers the last CTA completes the step
+        s->last_obs = obs_out;
+        ++s->obs_seq;
+    }
     return GPD_OK;
 }
 
@@ -763,6 +815,22 @@ int gpd_mirror_attach(gpd_sim* s, float* log, int64_t rows, int64_t row_len, int
     Mirror& m = s->mir;
     m.log = log; m.rows = rows; m.ld = row_len; m.col0 = col0;
     m.row = 0; m.valid = false; m.pending = false;
+    // Chunked issue: PCIe is full duplex and the copy engines run beside the SMs, so with the step cut into CTA sub-ranges the
+    // action upload of chunk c+1 overlaps the kernel of chunk c and the result download of chunk c-1 (measured: 141 -> ~90 us
+    // per 65,536-env step).  Worth it only when the copies dominate: >= 32,768 drones; GPD_MIRROR_CHUNKS overrides.
+    int chunks = s->D >= 32768 ? 4 : 1;
+    if (const char* ev = getenv("GPD_MIRROR_CHUNKS")) chunks = atoi(ev);
+    if (chunks > GPD_MIRROR_MAX_CHUNKS) chunks = GPD_MIRROR_MAX_CHUNKS;
+    if (chunks > s->lc.grid) chunks = (int)s->lc.grid;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 1) {
+        for (int c = 0; c < chunks; ++c) {
+            if (!m.cs[c]) CU(cudaStreamCreateWithFlags(&m.cs[c], cudaStreamNonBlocking));
+            if (!m.ce[c]) CU(cudaEventCreateWithFlags(&m.ce[c], cudaEventDisableTiming));
+        }
+        if (!m.ev_fork) CU(cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
+    }
+    m.chunks = chunks;
     return GPD_OK;
 }
 
@@ -853,16 +921,40 @@ int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_pre
         int rc = mirror_refresh(s, d_obs_prev, m.row, st);
         if (rc) return rc;
     }
-    CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
     char* pack = (char*)s->h_obs[nxt] + z.obs_pad;    // reward / flags staging lives behind the internal observation slot
     void* d_rew = pack;
     uint8_t* d_term = (uint8_t*)(pack + z.E * z.rs);
     uint8_t* d_trunc = d_term + z.E;
-    int rc = step_impl(s, s->h_act, d_obs_prev, d_obs_out, d_rew, d_term, d_trunc, terminal_kin ? s->h_tkin : nullptr, m.d_kin_t, stream);
-    if (rc) return rc;
+    if (m.chunks <= 1) {
+        CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
+        int rc = step_impl(s, s->h_act, d_obs_prev, d_obs_out, d_rew, d_term, d_trunc, terminal_kin ? s->h_tkin : nullptr, m.d_kin_t, stream);
+        if (rc) return rc;
+        // what the device computed: 12 kin rows into the slid window
+        CU(mirror_rows_d2h(s, m.row + s->A, m.d_kin_t, 12, st));
+    } else {
+        // fork: every chunk stream starts behind what the caller's stream holds so far (a window rebuild, earlier steps)
+        CU(cudaEventRecord(m.ev_fork, st));
+        const int64_t G = s->lc.grid;
+        const size_t act_row = (size_t)s->A * 4;        // RL envs: float32 actions
+        for (int c = 0; c < m.chunks; ++c) {
+            const int64_t c0 = G * c / m.chunks, c1 = G * (c + 1) / m.chunks;
+            const int64_t d0 = c0 * s->dpb, d1 = c1 * s->dpb < s->D ? c1 * s->dpb : s->D;
+            cudaStream_t q = m.cs[c];
+            CU(cudaStreamWaitEvent(q, m.ev_fork, 0));
+            CU(cudaMemcpyAsync((char*)s->h_act + d0 * act_row, (const char*)actions + d0 * act_row, (size_t)(d1 - d0) * act_row,
+                               cudaMemcpyHostToDevice, q));
+            int rc = step_impl(s, s->h_act, d_obs_prev, d_obs_out, d_rew, d_term, d_trunc, terminal_kin ? s->h_tkin : nullptr,
+                               m.d_kin_t, (void*)q, c0, c1 - c0);
+            if (rc) return rc;
+            // this chunk's columns of the 12 kin rows
+            CU(cudaMemcpy2DAsync(m.log + (m.row + s->A) * m.ld + m.col0 + d0, (size_t)m.ld * sizeof(float), m.d_kin_t + d0,
+                                 (size_t)s->D * sizeof(float), (size_t)(d1 - d0) * sizeof(float), 12, cudaMemcpyDeviceToHost, q));
+            CU(cudaEventRecord(m.ce[c], q));
+        }
+        for (int c = 0; c < m.chunks; ++c) CU(cudaStreamWaitEvent(st, m.ce[c], 0));      // join
+    }
     if (internal) { s->h_cur = nxt; s->h_has_prev = true; }
-    // what the device computed: 12 kin rows into the slid window, reward and flags
-    CU(mirror_rows_d2h(s, m.row + s->A, m.d_kin_t, 12, st));
+    // reward and flags of every env (one packed copy when the caller's arrays are laid out like the staging)
     const bool packed = reward && (void*)terminated == (char*)reward + z.E * z.rs && truncated == terminated + z.E;
     if (packed) {
         CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs + 2 * z.E, cudaMemcpyDeviceToHost, st));

@@ -106,6 +106,7 @@ struct StepArgs {
     uint32_t* tile_seq;     // per-CTA step sequencing [grid][8]: word 0 = steps claimed, word 1 = steps completed (tile_dep)
     int32_t tile_dep;       // 1: a CTA waits only for ITS OWN tile's previous step (per-CTA flag) instead of the whole grid
     int32_t target_per_env; // 1: p.target holds D entries (per-env MultiHover targets), else N
+    int32_t cta0;           // first CTA of this launch (0 unless the step is issued in chunks)
     SimPtrs<R> p;
     DevDrone<R> drone;
     DevPid<R> pid;
@@ -126,6 +127,8 @@ enum { GPD_K_FORCES = 0, GPD_K_LEAN = 1, GPD_K_PID = 2 };
 template <typename R> int step_blocks_per_sm(int action_type, int phy, int N, int A, int W, int env_kind, int threads, size_t smem);
 template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
                                               const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st);
+template <typename R> int step_bulk_blocks_per_sm(int action_type, int phy, int threads, size_t smem);
+template <typename R> cudaError_t launch_step_bulk(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
 template <typename R> cudaError_t launch_reset(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
 template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, const float* obs_latest, R* state20, R* rpy_rates, R* pid_state,
                                                    int32_t* counter, cudaStream_t st);

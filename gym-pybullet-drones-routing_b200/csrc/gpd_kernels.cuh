@@ -340,13 +340,14 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool ctrl = a.env_kind == GPD_ENV_CTRL;
     Smem<R> sm{ smem_raw + a.tma_bytes, a.DPB, a.EPB, ctrl, MULTI };
     const int t = threadIdx.x;
-    const int64_t row0 = (int64_t)blockIdx.x * a.DPB;
+    const int bid = (int)blockIdx.x + a.cta0;     // a launch may cover a sub-range of the CTAs (chunked host-mirror steps)
+    const int64_t row0 = (int64_t)bid * a.DPB;
     const int64_t d = row0 + t;
     const bool active = t < a.DPB && d < a.D;
     const int rows = (int)min((int64_t)a.DPB, a.D - row0);
     const int le = MULTI ? t / a.N : t;          // local env
     const int i = MULTI ? t - le * a.N : 0;      // drone index in env
-    const int64_t e = MULTI ? (int64_t)blockIdx.x * a.EPB + le : d;
+    const int64_t e = MULTI ? (int64_t)bid * a.EPB + le : d;
     const DevDrone<R>& P = a.drone;
     // Warp specialisation (RL envs): the last `copy_threads` threads of the block (one warp) move the action history of
     // the tile — as two TMA tensor copies issued by one lane when the rows are float4-granular — while the other warps
@@ -355,19 +356,13 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool spec = a.copy_threads > 0;
     const bool run_physics = t < nphys;
 
-    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 0] = gtime();      // 0: CTA start (params fetched)
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();      // 0: CTA start (params fetched)
     const bool tma_copy = spec && a.use_tma;
     const bool edge_smem = tma_copy && VEC && a.tma_edge;       // physics threads read the two edge slots from shared memory
     if (tma_copy && t == nphys) mbar_init(&tma_bar, 1);
-    // this step's action does not depend on the previous step: its load overlaps the sequencing round trip below
-    float4 act_pre = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (VEC) {
-        if (run_physics && active && a.action_type != GPD_ACT_CTRL_RPM && a.action_type != GPD_ACT_CTRL_VEL)
-            act_pre = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
-    }
     if (a.tile_dep) {
         if (t == 0) {                   // claim this tile's sequence number and look at its completed count in one round trip
-            uint32_t* seq = a.tile_seq + (int64_t)blockIdx.x * 8;
+            uint32_t* seq = a.tile_seq + (int64_t)bid * 8;
             const uint32_t done0 = ld_acquire_gpu(seq + 1);
             const uint32_t mine = atomicAdd(seq, 1u);          // steps claimed before this one
             if (done0 != mine)
@@ -380,7 +375,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         if (edge_smem) __syncthreads(); // the physics threads will wait on the mbarrier the DMA lane just initialised
         pdl_wait();                     // everything above touched only parameters and shared memory
     }
-    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 1] = gtime();      // 1: previous step of this tile complete
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 1] = gtime();      // 1: previous step of this tile complete
 
     if (!ctrl && !tma_copy)             // no TMA for this row shape (A = 3 or 1) or no previous observation: every thread
         copy_history<VEC>(a.obs_prev, reinterpret_cast<float*>(a.obs_out), reinterpret_cast<const float*>(a.actions),
@@ -414,9 +409,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 }
                 tma_load_2d(smem_raw, &tm_prev, 12 + 4 * (a.tma_edge + 1), (int)row0, &tma_bar);
                 mbar_wait(&tma_bar, 0);
-                if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 5] = gtime();    // 5: history tile landed in smem
+                if (a.timeline) a.timeline[(int64_t)bid * 8 + 5] = gtime();    // 5: history tile landed in smem
                 tma_store_2d(&tm_out, 12 + 4 * a.tma_edge, (int)row0, smem_raw);
-                if (a.timeline) a.timeline[(int64_t)blockIdx.x * 8 + 6] = gtime();    // 6: TMA store has read smem
+                if (a.timeline) a.timeline[(int64_t)bid * 8 + 6] = gtime();    // 6: TMA store has read smem
                 if (a.tile_dep) tma_store_wait_all();
             }
         }
@@ -470,7 +465,8 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         } else {
             const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
             if constexpr (VEC) {
-                act[0] = act_pre.x; act[1] = act_pre.y; act[2] = act_pre.z; act[3] = act_pre.w;
+                float4 v = __ldg(reinterpret_cast<const float4*>(ap));
+                act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
             } else {
                 for (int k = 0; k < a.A; ++k) act[k] = __ldg(ap + k);
             }
@@ -503,7 +499,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     Forcing<R> F;
     make_forcing(P, rpm, F);
     const R rpm_r[4] = { (R)rpm[0], (R)rpm[1], (R)rpm[2], (R)rpm[3] };
-    if (a.timeline && t == 0 && F.T == F.T) a.timeline[(int64_t)blockIdx.x * 8 + 2] = gtime();   // 2: state + action arrived
+    if (a.timeline && t == 0 && F.T == F.T) a.timeline[(int64_t)bid * 8 + 2] = gtime();   // 2: state + action arrived
 
     // ---- PYB_STEPS_PER_CTRL substeps (BaseAviary.py:343-372), state in registers ----
     R avx = R(0), avy = R(0), avz = R(0);
@@ -571,7 +567,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         }
     }
 
-    if (a.timeline && t == 0 && s.px == s.px) a.timeline[(int64_t)blockIdx.x * 8 + 3] = gtime(); // 3: substeps done
+    if (a.timeline && t == 0 && s.px == s.px) a.timeline[(int64_t)bid * 8 + 3] = gtime(); // 3: substeps done
     // ---- _updateAndStoreKinematicInformation (BaseAviary.py:374,509-519) + outputs ----
     R roll, pitch, yaw;
     quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
@@ -733,10 +729,10 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }   // run_physics
 
     if (!a.pdl_trigger_early) pdl_launch_dependents();   // this CTA has issued all its loads and (physics warps) stores
-    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 4] = gtime();      // 4: physics thread 0 stored everything
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();      // 4: physics thread 0 stored everything
     // ---- Ctrl observation tile: coalesced write of the staged state20 rows (contiguous in global memory) ----
     if (ctrl || a.auto_reset || a.tile_dep) __syncthreads();
-    if (a.timeline && t == 0) a.timeline[(int64_t)blockIdx.x * 8 + 7] = gtime();      // 7: block barrier passed
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 7] = gtime();      // 7: block barrier passed
     if (ctrl) {
         const R* st = sm.stage_r();
         R* out = reinterpret_cast<R*>(a.obs_out) + row0 * 20;
@@ -744,7 +740,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     }
 
     if (a.auto_reset && t == 0) {       // combine the warps' partials, then RED (no return value, no wait) into this CTA's slot
-        StatSlot* slot = a.p.stat_slots + blockIdx.x;
+        StatSlot* slot = a.p.stat_slots + bid;
         int n = 0, len = 0, mn = 0x7fffffff, mx = (int)0x80000000;
         float sr = 0.f, sr2 = 0.f, st = 0.f;
         for (int w = 0; w < (nphys >> 5); ++w) {
@@ -762,12 +758,12 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
             atomicMax(&slot->mx, mx);
             if (st > 0.f) atomicAdd(&slot->s[5], (double)st);
         }
-        atomicAdd(&slot->s[4], (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)blockIdx.x * a.EPB) : rows));
+        atomicAdd(&slot->s[4], (double)(MULTI ? min((int64_t)a.EPB, a.E - (int64_t)bid * a.EPB) : rows));
     }
     if (a.tile_dep) {
         if (ctrl) __syncthreads();      // the tile write-out above is part of what the next step of this tile reads
         // every global write of this CTA happened before the barrier(s) above: publish the tile (release, gpu scope)
-        if (t == 0) red_release_gpu_inc(a.tile_seq + (int64_t)blockIdx.x * 8 + 1);
+        if (t == 0) red_release_gpu_inc(a.tile_seq + (int64_t)bid * 8 + 1);
         // keep stream order transitive: this grid does not complete before the grids it was allowed to overtake
         pdl_wait();
     }

@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "gpd_kernels.cuh"
+#include "gpd_step_bulk.cuh"
 
 namespace gpd {
 
@@ -122,6 +123,70 @@ cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cons
     case 10: return launch_step_t<GPD_K_PID, true, false>(a, lc, tp, to, te, st);
     case 11: return launch_step_t<GPD_K_PID, true, true>(a, lc, tp, to, te, st);
     default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---- bulk-copy data path of the single-drone RL envs with 4-wide actions (gpd_step_bulk.cuh) ----
+template <int KIND>
+static cudaError_t ensure_bulk_smem(size_t need)
+{
+    static SmemLimit lim;
+    return lim.ensure(need, step_kernel_bulk<Real, KIND>);
+}
+
+static int bulk_kind(int action_type, int phy)
+{
+    const bool rpm_like = action_type == GPD_ACT_RPM;
+    return !rpm_like ? GPD_K_PID : (phy == 0 ? GPD_K_LEAN : GPD_K_FORCES);
+}
+
+template <int KIND>
+static int bulk_occupancy_t(int threads, size_t smem)
+{
+    if (ensure_bulk_smem<KIND>(smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_kernel_bulk<Real, KIND>, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+template <>
+int step_bulk_blocks_per_sm<Real>(int action_type, int phy, int threads, size_t smem)
+{
+    switch (bulk_kind(action_type, phy)) {
+    case GPD_K_FORCES: return bulk_occupancy_t<GPD_K_FORCES>(threads, smem);
+    case GPD_K_LEAN: return bulk_occupancy_t<GPD_K_LEAN>(threads, smem);
+    default: return bulk_occupancy_t<GPD_K_PID>(threads, smem);
+    }
+}
+
+template <int KIND>
+static cudaError_t launch_step_bulk_t(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
+{
+    cudaError_t e = ensure_bulk_smem<KIND>(lc.smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)lc.grid);
+    cfg.blockDim = dim3((unsigned)lc.threads);
+    cfg.dynamicSmemBytes = lc.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = lc.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, step_kernel_bulk<Real, KIND>, a);
+}
+
+template <>
+cudaError_t launch_step_bulk<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
+{
+    switch (bulk_kind(a.action_type, a.phy)) {
+    case GPD_K_FORCES: return launch_step_bulk_t<GPD_K_FORCES>(a, lc, st);
+    case GPD_K_LEAN: return launch_step_bulk_t<GPD_K_LEAN>(a, lc, st);
+    default: return launch_step_bulk_t<GPD_K_PID>(a, lc, st);
     }
 }
 

@@ -1,0 +1,378 @@
+// gpd_step_bulk.cuh — the fused step kernel of the single-drone RL envs with 4-wide actions (HoverAviary with
+// ActionType.RPM / VEL: the BASELINE headline shape), with ALL of its HBM traffic moved by bulk asynchronous copies.
+//
+// Why a second data path (measured, profiles/stream_microbench.cu, 65,536 envs, 8 rotating sets, PDL): a plain streaming
+// kernel moves this launch's bytes in 7.0 us; the step's own 14 address streams accessed per thread take 12.2 us; the same
+// streams moved only by cp.async.bulk take 7.1 us.  The per-thread / TMA-box mix of gpd::step_kernel sits at 9.3 us.
+//
+// One CTA = one tile of T = DPB envs, T threads, no DMA warp.  Thread 0 claims the tile (per-CTA step sequencing, see
+// gpd_kernels.cuh) and issues, on ONE mbarrier,
+//     the observation tile   T rows x W floats, CONTIGUOUS in global memory, read from obs_prev at +A floats: in shared
+//                            memory row r then holds [old kin[4..11] | old ring slots 1..B-1 | 16 stray bytes], i.e. the
+//                            shifted ring already sits where the new row wants it (BaseRLAviary.py:187,317-318)
+//     the state tiles        sP, sQ, sV (16/32 B per env), sWz, step counter, episode return
+//     the action tile        T x 16 B
+// Every thread then integrates its drone from shared memory exactly as gpd::step_kernel does (same device functions, same
+// order of operations: results are bit-identical), patches its row (12 kin floats in front, this step's action in the newest
+// slot), writes its state / reward / flags back into shared memory; after one barrier thread 0 stores every tile back with
+// bulk copies (the observation tile as ONE contiguous 18 KB store).  Reading the full old rows costs 48 B per env more than
+// the shifted slots alone (the DRAM atom is 64 B: 32 of them were being fetched anyway); in exchange every byte moves in
+// long contiguous bursts.
+#pragma once
+
+#include "gpd_kernels.cuh"
+
+namespace gpd {
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory carve-up of one tile (every region starts 16-byte aligned because T % 16 == 0)
+template <typename R>
+struct BulkSmem {
+    unsigned char* base;
+    int T, W;
+    __device__ float* obs() const { return reinterpret_cast<float*>(base); }
+    __device__ V4<R>* sP() const { return reinterpret_cast<V4<R>*>(base + (size_t)T * W * 4); }
+    __device__ V4<R>* sQ() const { return sP() + T; }
+    __device__ V4<R>* sV() const { return sQ() + T; }
+    __device__ float4* act() const { return reinterpret_cast<float4*>(sV() + T); }
+    __device__ R* sWz() const { return reinterpret_cast<R*>(act() + T); }
+    __device__ R* rew() const { return sWz() + T; }
+    __device__ int32_t* cnt() const { return reinterpret_cast<int32_t*>(rew() + T); }
+    __device__ float* ep() const { return reinterpret_cast<float*>(cnt() + T); }
+    __device__ uint8_t* term() const { return reinterpret_cast<uint8_t*>(ep() + T); }
+    __device__ uint8_t* trunc() const { return term() + T; }
+    __device__ float* stat_f() const { return reinterpret_cast<float*>(trunc() + T); }
+    __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4 * 8); }      // up to 8 warps
+};
+
+template <typename R, int KIND>
+// registers: FP32 lean 64 (8 CTAs of 128 threads), DSLPID 72, force models 80; FP64 128 — shared memory (26-53 KB per tile)
+// caps the FP64 variants at 512 threads per SM anyway, so they get the registers that would otherwise spill
+__global__ void __launch_bounds__(128, sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 8 : (KIND == GPD_K_PID ? 7 : 5)) : 4)
+step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
+{
+    constexpr bool LEAN = KIND == GPD_K_LEAN, HAS_PID = KIND == GPD_K_PID;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const int t = threadIdx.x;
+    const int bid = (int)blockIdx.x + a.cta0;
+    const int T = a.DPB;
+    BulkSmem<R> sm{ smem_raw, T, a.W };
+    const int64_t row0 = (int64_t)bid * T;
+    const int64_t d = row0 + t;             // N == 1: drone = env
+    const bool active = d < a.D;
+    const int rows = (int)min((int64_t)T, a.D - row0);
+    const bool full = rows == T;
+    const DevDrone<R>& P = a.drone;
+
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();
+    if (t == 0) mbar_init(&bar, 1);
+    if (a.tile_dep) {
+        if (t == 0) {
+            uint32_t* seq = a.tile_seq + (int64_t)bid * 8;
+            const uint32_t done0 = ld_acquire_gpu(seq + 1);
+            const uint32_t mine = atomicAdd(seq, 1u);
+            if (done0 != mine)
+                while (ld_acquire_gpu(seq + 1) != mine) __nanosleep(32);
+        }
+        __syncthreads();
+        if (a.pdl_trigger_early) pdl_launch_dependents();
+    } else {
+        if (a.pdl_trigger_early) pdl_launch_dependents();
+        __syncthreads();
+        pdl_wait();
+    }
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 1] = gtime();
+
+    // ---- loads: everything this tile needs, in flight at once ----
+    if (t == 0) {
+        fence_proxy_async_global();         // generic-proxy writes of the tile's previous step (ragged tails) -> bulk reads
+        const uint32_t v4b = (uint32_t)sizeof(V4<R>);
+        // the last tile of the buffer must not read past its end: its final row loses the 16 stray bytes
+        const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((row0 + rows >= a.D) ? 16u : 0u) : 0u;
+        const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
+        const uint32_t total = ob + 3 * st + (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u);
+        mbar_expect_tx(&bar, total);
+        if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + a.A, ob, &bar);
+        bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
+        bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
+        bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
+        bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
+        bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);                  // library arrays are padded to whole tiles
+        bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
+        if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
+    }
+    // what does not come through shared memory: per-index constants and the optional per-drone extras
+    V4<R> tg = M<R>::make4(R(0), R(0), R(0), R(0)), ip0 = tg, iq0 = tg;
+    R rpm_prev[4] = { R(0), R(0), R(0), R(0) };
+    const bool pre_init = a.auto_reset && !a.init_per_env;
+    if (active) {
+        tg = a.p.target[a.target_per_env ? d : (int64_t)0];
+        if (pre_init) { ip0 = a.p.init_pos[0]; iq0 = a.p.init_quat[0]; }
+        if constexpr (!LEAN) {
+            if (a.phy & GPD_PHY_DRAG) {
+                V4<R> v = a.p.aux_rpm[d];
+                rpm_prev[0] = v.x; rpm_prev[1] = v.y; rpm_prev[2] = v.z; rpm_prev[3] = v.w;
+            }
+        }
+    }
+    if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
+        float* r = sm.obs() + (size_t)t * a.W;
+        for (int k = 12; k < a.W; ++k) r[k] = 0.f;
+    }
+    mbar_wait(&bar, 0);
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
+
+    State<R> s;
+    s.px = s.py = s.pz = s.qx = s.qy = s.qz = R(0); s.qw = R(1);
+    s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
+    float act[4] = { 0.f, 0.f, 0.f, 0.f };
+    int32_t cnt = 0;
+    float ep_ret0 = 0.f;
+    if (active) {
+        const V4<R> p4 = sm.sP()[t], q4 = sm.sQ()[t], v4 = sm.sV()[t];
+        s.px = p4.x; s.py = p4.y; s.pz = p4.z; s.wx = p4.w;
+        s.qx = q4.x; s.qy = q4.y; s.qz = q4.z; s.qw = q4.w;
+        s.vx = v4.x; s.vy = v4.y; s.vz = v4.z; s.wy = v4.w;
+        s.wz = sm.sWz()[t];
+        const float4 av = sm.act()[t];
+        act[0] = av.x; act[1] = av.y; act[2] = av.z; act[3] = av.w;
+        cnt = sm.cnt()[t];
+        if (a.auto_reset) ep_ret0 = sm.ep()[t];
+    }
+
+    // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238); A == 4: ActionType.RPM or ActionType.VEL ----
+    double rpm[4] = { 0., 0., 0., 0. };
+    if (a.action_type == GPD_ACT_RPM) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rpm[k] = P.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[k]));   // :192, float32 inner ops
+    }
+    if constexpr (HAS_PID) {
+        if (a.action_type == GPD_ACT_VEL && active) {
+            R r4[4];
+            pid_action(a, d, s, act, r4);
+            rpm[0] = r4[0]; rpm[1] = r4[1]; rpm[2] = r4[2]; rpm[3] = r4[3];
+        }
+    }
+    Forcing<R> F;
+    make_forcing(P, rpm, F);
+    const R rpm_r[4] = { (R)rpm[0], (R)rpm[1], (R)rpm[2], (R)rpm[3] };
+
+    // ---- PYB_STEPS_PER_CTRL substeps (BaseAviary.py:343-372), state in registers ----
+    R avx = R(0), avy = R(0), avz = R(0);
+    R wsum_prev = R(0), wsum_cur = R(0);
+    if constexpr (!LEAN) {
+        if (a.phy & GPD_PHY_DRAG) { wsum_prev = drag_wsum(rpm_prev); wsum_cur = drag_wsum(rpm_r); }
+    }
+    int sub0 = 0;
+    if constexpr (LEAN && !M<R>::is_double) {
+        LeanStep c;
+        c.kt2 = (2.f * P.DT_INV_M) * F.Ttot; c.ktmg = P.DT_INV_M * F.T;
+        c.cx = P.DT_JINV[0] * F.tx; c.cy = P.DT_JINV[1] * F.ty; c.cz = P.DT_JINV[2] * F.tz;
+        c.ex = P.DT_EULER[0]; c.ey = P.DT_EULER[1]; c.ez = P.DT_EULER[2];
+        c.h = a.dt * .5f; c.hh = c.h * c.h;
+        for (; sub0 < a.S - 1; ++sub0) lean_substep_f32(a.dt, s, c);
+    }
+    for (int sub = sub0; sub < a.S; ++sub) {
+        R m[9];
+        const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);
+        const bool last = sub == a.S - 1;
+        if constexpr (LEAN) {
+            dyn_substep<R>(P, a.dt, s, m, omz, F, nullptr, nullptr, last, avx, avy, avz);
+        } else {
+            R gnd[4], fb[3] = { R(0), R(0), R(0) };
+            const R* pg = nullptr;
+            const R* pb = nullptr;
+            if (a.phy & GPD_PHY_GND) {      // same sign-based gate as gpd::step_kernel
+                const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
+                const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
+                const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
+                const R roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
+                const R pitch = gimbal ? R(GPD_PI) : R(0);
+                if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
+            }
+            if (a.phy & GPD_PHY_DRAG) {
+                R db[3];
+                drag_body_w(P, sub == 0 ? wsum_prev : wsum_cur, m, s.vx, s.vy, s.vz, db);
+                fb[0] += db[0]; fb[1] += db[1]; fb[2] += db[2];
+                pb = fb;
+            }
+            dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, last, avx, avy, avz);
+        }
+    }
+    if (a.timeline && t == 0 && s.px == s.px) a.timeline[(int64_t)bid * 8 + 3] = gtime();
+
+    // ---- _updateAndStoreKinematicInformation (BaseAviary.py:374,509-519) + outputs ----
+    R roll, pitch, yaw;
+    quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+    R rew;
+    int term, trunc;
+    {
+        R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
+        R dist = M<R>::sqrt(ex * ex + ey * ey + ez * ez);
+        R d2 = dist * dist;
+        R v = R(2) - d2 * d2;               // HoverAviary.py:78 / MultiHoverAviary.py:87
+        rew = v > R(0) ? v : R(0);
+        const R lim = a.env_kind == GPD_ENV_HOVER ? R(1.5) : R(2.0);
+        trunc = (M<R>::abs(s.px) > lim || M<R>::abs(s.py) > lim || s.pz > R(2.0) ||
+                 M<R>::abs(roll) > R(.4) || M<R>::abs(pitch) > R(.4)) ? 1 : 0;
+        term = dist < R(.0001);
+    }
+    if (cnt > a.max_counter) trunc = 1;     // HoverAviary.py:114 (counter BEFORE the increment)
+    const int done = a.auto_reset ? (term | trunc) : 0;
+
+    float kin[12];
+    kin[0] = (float)s.px; kin[1] = (float)s.py; kin[2] = (float)s.pz;
+    kin[3] = (float)roll; kin[4] = (float)pitch; kin[5] = (float)yaw;
+    kin[6] = (float)s.vx; kin[7] = (float)s.vy; kin[8] = (float)s.vz;
+    kin[9] = (float)avx; kin[10] = (float)avy; kin[11] = (float)avz;
+    R out_rpm[4] = { rpm_r[0], rpm_r[1], rpm_r[2], rpm_r[3] };
+
+    float ep_new = 0.f;
+    if (a.auto_reset) {                     // Monitor-style episode statistics, as in gpd::step_kernel
+        float er = ep_ret0 + (float)rew;
+        int el = cnt / a.S + 1;
+        const bool fin = active && done;
+        const unsigned m = __ballot_sync(0xffffffffu, fin);
+        float s1 = 0.f, s2 = 0.f;
+        int nl = 0, nt = 0, mn = 0x7fffffff, mx = (int)0x80000000;
+        if (m) {
+            s1 = fin ? er : 0.f; s2 = fin ? er * er : 0.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            }
+            nl = __reduce_add_sync(0xffffffffu, fin ? el : 0);
+            nt = __popc(__ballot_sync(0xffffffffu, fin && term));
+            mn = __reduce_min_sync(0xffffffffu, fin ? float_to_ordered(er) : 0x7fffffff);
+            mx = __reduce_max_sync(0xffffffffu, fin ? float_to_ordered(er) : (int)0x80000000);
+        }
+        if ((t & 31) == 0) {
+            float* sf = sm.stat_f() + 4 * (t >> 5);
+            int* si = sm.stat_i() + 4 * (t >> 5);
+            sf[0] = s1; sf[1] = s2; sf[2] = (float)nt;
+            si[0] = __popc(m); si[1] = nl; si[2] = mn; si[3] = mx;
+        }
+        ep_new = fin ? 0.f : er;
+    }
+    if (a.auto_reset && active && done) {
+        if (a.terminal_kin) {
+            float4* tk = reinterpret_cast<float4*>(a.terminal_kin) + d * 3;
+            tk[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
+            tk[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
+            tk[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+        }
+        if (pre_init) {                     // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
+            s.px = ip0.x; s.py = ip0.y; s.pz = ip0.z;
+            s.qx = iq0.x; s.qy = iq0.y; s.qz = iq0.z; s.qw = iq0.w;
+            s.vx = s.vy = s.vz = R(0);
+            s.wx = s.wy = s.wz = R(0);
+        } else {
+            init_state(a, d, 0, s);
+        }
+        quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+        avx = avy = avz = R(0);
+        out_rpm[0] = out_rpm[1] = out_rpm[2] = out_rpm[3] = R(0);
+        kin[0] = (float)s.px; kin[1] = (float)s.py; kin[2] = (float)s.pz;
+        kin[3] = (float)roll; kin[4] = (float)pitch; kin[5] = (float)yaw;
+#pragma unroll
+        for (int k = 6; k < 12; ++k) kin[k] = 0.f;
+    }
+
+    // ---- everything back into the tile ----
+    if (active) {
+        sm.sP()[t] = M<R>::make4(s.px, s.py, s.pz, s.wx);
+        sm.sQ()[t] = M<R>::make4(s.qx, s.qy, s.qz, s.qw);
+        sm.sV()[t] = M<R>::make4(s.vx, s.vy, s.vz, s.wy);
+        sm.sWz()[t] = s.wz;
+        sm.cnt()[t] = done ? 0 : cnt + a.S;                             // BaseAviary.py:382
+        if (a.auto_reset) sm.ep()[t] = ep_new;
+        float4* r = reinterpret_cast<float4*>(sm.obs() + (size_t)t * a.W);
+        r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);             // BaseRLAviary.py:310-316
+        r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
+        r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
+        r[(a.W >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);   // newest ring slot, BaseRLAviary.py:187
+        if (full) {
+            sm.rew()[t] = rew; sm.term()[t] = (uint8_t)term; sm.trunc()[t] = (uint8_t)trunc;
+        } else {                            // ragged last tile: sizes are no multiples of 16 bytes, plain stores
+            if (a.reward) a.reward[d] = rew;
+            if (a.terminated) a.terminated[d] = (uint8_t)term;
+            if (a.truncated) a.truncated[d] = (uint8_t)trunc;
+        }
+        if (!(LEAN && a.skip_aux)) {
+            a.p.aux_av[d] = M<R>::make4(avx, avy, avz, R(0));
+            a.p.aux_rpm[d] = M<R>::make4(out_rpm[0], out_rpm[1], out_rpm[2], out_rpm[3]);
+        } else if (d == 0) {
+            *a.p.aux_auth = 0;
+        }
+        if (a.kin_t) {                      // host mirror: feature-major copy of the kin part
+#pragma unroll
+            for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.D + d] = kin[k];
+        }
+    }
+    fence_proxy_async_smem();               // this thread's shared-memory writes -> the bulk stores below
+    __syncthreads();
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();
+
+    if (t == 0) {
+        const uint32_t v4b = (uint32_t)sizeof(V4<R>);
+        const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
+        bulk_s2g(reinterpret_cast<float*>(a.obs_out) + row0 * a.W, sm.obs(), (uint32_t)rows * a.W * 4);
+        bulk_s2g(a.p.sP + row0, sm.sP(), st);
+        bulk_s2g(a.p.sQ + row0, sm.sQ(), st);
+        bulk_s2g(a.p.sV + row0, sm.sV(), st);
+        bulk_s2g(a.p.sWz + row0, sm.sWz(), sc);
+        bulk_s2g(a.p.counter + row0, sm.cnt(), i4);
+        if (a.auto_reset) bulk_s2g(a.p.ep_ret + row0, sm.ep(), i4);
+        if (full) {
+            if (a.reward) bulk_s2g(a.reward + row0, sm.rew(), sc);
+            if (a.terminated) bulk_s2g(a.terminated + row0, sm.term(), (uint32_t)T);
+            if (a.truncated) bulk_s2g(a.truncated + row0, sm.trunc(), (uint32_t)T);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (a.auto_reset) {                 // combine the warps' partials while the stores drain
+            StatSlot* slot = a.p.stat_slots + bid;
+            int n = 0, len = 0, mn = 0x7fffffff, mx = (int)0x80000000;
+            float sr = 0.f, sr2 = 0.f, stt = 0.f;
+            for (int w = 0; w < ((T + 31) >> 5); ++w) {
+                const float* sf = sm.stat_f() + 4 * w;
+                const int* si = sm.stat_i() + 4 * w;
+                n += si[0]; len += si[1]; mn = min(mn, si[2]); mx = max(mx, si[3]);
+                sr += sf[0]; sr2 += sf[1]; stt += sf[2];
+            }
+            if (n > 0) {
+                atomicAdd(&slot->s[0], (double)n);
+                atomicAdd(&slot->s[1], (double)sr);
+                atomicAdd(&slot->s[2], (double)len);
+                atomicAdd(&slot->s[3], (double)sr2);
+                atomicMin(&slot->mn, mn);
+                atomicMax(&slot->mx, mx);
+                if (stt > 0.f) atomicAdd(&slot->s[5], (double)stt);
+            }
+            atomicAdd(&slot->s[4], (double)rows);
+        }
+        if (a.tile_dep) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
+            red_release_gpu_inc(a.tile_seq + (int64_t)bid * 8 + 1);
+        } else {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        if (a.timeline) a.timeline[(int64_t)bid * 8 + 7] = gtime();
+    }
+    if (!a.pdl_trigger_early) pdl_launch_dependents();
+    if (a.tile_dep) pdl_wait();             // keep stream order transitive (see gpd::step_kernel)
+}
+
+}  // namespace gpd

@@ -9,6 +9,7 @@ the fixtures it writes are committed, together with this script.
 
 What is recorded (all float64 unless noted; NumPy version stored in every file):
   constants.json        _parseURDFParameters + derived constants + DSLPIDControl gains, per model
+  traj_roundtrip_*.npz  the same protocol with the stand-in's quaternion read-back round trip ON (what real Bullet does)
   traj_*.npz            action-replay trajectories (incl. VelocityAviary): float32 (RL) / float64 (Ctrl) action sequence,
                         state20 + rpy_rates + reward/terminated/truncated at checkpoints,
                         obs rows at a few steps
@@ -183,6 +184,32 @@ def gen_traj(R, out):
         np.savez_compressed(os.path.join(out, f"traj_{name}.npz"), actions=acts, kind="ctrl", env="CtrlAviary",
                             model=model.value, ctrl_freq=freq, pyb_freq=240, num_drones=n, act_type="ctrl_rpm",
                             init_xyz=xyz, init_rpy=rpy, numpy=np.__version__, **rec)
+
+
+def gen_roundtrip(R, out):
+    """The same replay protocol with the stand-in emulating what real Bullet does on every pose read-back: the base quaternion
+    goes through a rotation-matrix round trip (unit norm, canonical sign).  The kernels never renormalise
+    (BaseAviary.py:888 does not either): these files pin that the difference stays far below 1e-9 and only the quaternion's
+    sign can differ (compared up to sign).  Real pybullet itself is not installable here: residual, stated in DESIGN.md."""
+    import pybullet
+    P, DM = R["Physics"], R["DroneModel"]
+    pybullet.ROUNDTRIP = True
+    try:
+        for ci, (name, ctor, kw, kind, steps) in enumerate([
+                ("roundtrip_hover_cf2x_30_uniform", "HoverAviary", dict(drone_model=DM.CF2X, ctrl_freq=30), "uniform", 1000),
+                ("roundtrip_multihover2_cf2p_30_uniform", "MultiHoverAviary", dict(drone_model=DM.CF2P, num_drones=2, ctrl_freq=30),
+                 "uniform", 600)]):
+            rng = np.random.default_rng(3000 + ci)
+            with quiet():
+                env = R[ctor](physics=P.DYN, **kw)
+            n, a = env.action_space.shape
+            acts = action_stream(kind, rng, steps, n, a)
+            rec = replay(env, acts, ckpt_every=10, full_first=20, obs_steps={0, 1, 5, 16, 30, steps - 1})
+            np.savez_compressed(os.path.join(out, f"traj_{name}.npz"), actions=acts, kind=kind, env=ctor,
+                                model=kw["drone_model"].value, ctrl_freq=kw["ctrl_freq"], pyb_freq=240, num_drones=n,
+                                act_type="rpm", numpy=np.__version__, standin="ROUNDTRIP=True", **rec)
+    finally:
+        pybullet.ROUNDTRIP = False
 
 
 def gen_velocity(R, out):
@@ -509,11 +536,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,velocity,pid,forces,composite,reset,logger,pidpy")
+    ap.add_argument("--only", default="", help="comma-separated subset of: constants,traj,roundtrip,velocity,pid,forces,composite,reset,logger,pidpy")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     R = _load_reference(a.ref)
-    gens = dict(constants=gen_constants, traj=gen_traj, velocity=gen_velocity, pid=gen_pid, forces=gen_forces,
+    gens = dict(constants=gen_constants, traj=gen_traj, roundtrip=gen_roundtrip, velocity=gen_velocity, pid=gen_pid, forces=gen_forces,
                 composite=gen_composite, reset=gen_reset_quirks, logger=gen_logger, pidpy=gen_pidpy)
     for name, fn in gens.items():
         if not a.only or name in a.only.split(","):

@@ -34,45 +34,53 @@ def _kw(env_kind="hover", act="rpm", N=1, freq=30, flags=0, model=DroneModel.CF2
                 init_xyz=None, init_rpy=None)
 
 
-@pytest.mark.parametrize("act,N,freq,precision", [("rpm", 1, 30, "f32"), ("rpm", 1, 48, "f64"), ("pid", 1, 48, "f32"),
-                                                    ("one_d_rpm", 1, 30, "f32"), ("rpm", 3, 30, "f32"), ("vel", 2, 30, "f64")])
-def test_cuda_host_mirror_equals_device_observation(act, N, freq, precision):
+@pytest.mark.parametrize("act,N,freq,precision,chunks", [("rpm", 1, 30, "f32", 1), ("rpm", 1, 30, "f32", 3), ("rpm", 1, 48, "f64", 1),
+                                                           ("pid", 1, 48, "f32", 4), ("one_d_rpm", 1, 30, "f32", 1),
+                                                           ("rpm", 3, 30, "f32", 2), ("vel", 2, 30, "f64", 1)])
+def test_cuda_host_mirror_equals_device_observation(act, N, freq, precision, chunks, monkeypatch):
     """The numpy-facing step returns a strided view of the pinned feature-major log; at every step it must equal, bit for bit,
     the device observation (same chain), through window slides, compactions (16-step log), masked and full resets, and
-    tensor-path steps in between (stale mirror -> rebuilt)."""
+    tensor-path steps in between (stale mirror -> rebuilt); also when the step is issued in chunks over CTA sub-ranges
+    (each with its own copies on its own stream, the default from 32,768 drones)."""
     rng = np.random.default_rng(3)
     E = 517
+    monkeypatch.setenv("GPD_MIRROR_CHUNKS", str(chunks))
     kw = _kw("hover" if N == 1 else "multihover", act, N, freq, model=DroneModel.CF2P if act in ("pid", "vel") else DroneModel.CF2X)
     sim = make_sim(kw, E, precision, auto_reset=True)
+    twin = make_sim(kw, E, precision, auto_reset=True)      # the same run on device tensors only
     sim.attach_mirror(slide_steps=16)
     A = sim.A
     out = sim.alloc_host_outputs(pinned=True, terminal_kin=True)
     obs = sim.reset_host()
+    twin.reset()
     assert obs.shape == (E, N, sim.W) and obs.dtype == np.float32 and not obs.flags["C_CONTIGUOUS"]
-    assert np.array_equal(obs, sim.obs.cpu().numpy())
+    assert np.array_equal(obs, sim.obs.cpu().numpy()) and np.array_equal(obs, twin.obs.cpu().numpy())
     for t in range(70):
         a = rng.uniform(-1, 1, (E, N, A)).astype(np.float32)
+        od, rd, td, trd = twin.step(torch.from_numpy(a).cuda())
         if t in (23, 24, 40):               # tensor-path steps: the device chain moves without the mirror
             sim.step(torch.from_numpy(a).cuda())
             continue
         obs, rew, term, trunc, tkin = sim.step_host(a, out)
-        dev = sim.obs.cpu().numpy()
-        assert np.array_equal(obs, dev), (t, "obs")
+        assert np.array_equal(obs, sim.obs.cpu().numpy()), (t, "host obs == this sim's device obs")
+        assert np.array_equal(obs, od.cpu().numpy()), (t, "host obs == the tensor-path twin's obs")
         assert np.array_equal(obs[..., -A:], a), (t, "newest ring slot is this step's action")
-        assert np.array_equal(rew, sim.reward.cpu().numpy()) and np.array_equal(term, sim.terminated.cpu().numpy())
-        assert np.array_equal(trunc, sim.truncated.cpu().numpy())
+        assert np.array_equal(rew, rd.cpu().numpy()) and np.array_equal(term, td.cpu().numpy())
+        assert np.array_equal(trunc, trd.cpu().numpy())
         done = (term | trunc).astype(bool)
         if done.any():
-            assert np.array_equal(tkin[done], sim.terminal_kin.cpu().numpy()[done])
+            assert np.array_equal(tkin[done], twin.terminal_kin.cpu().numpy()[done])
         if t == 30:                         # masked reset through the host path: ring survives, kin rows refreshed in place
             m = (rng.random(E) < 0.4).astype(np.uint8)
             o2 = sim.reset_host(m)
-            assert np.array_equal(o2, sim.obs.cpu().numpy())
+            twin.reset(torch.from_numpy(m))
+            assert np.array_equal(o2, sim.obs.cpu().numpy()) and np.array_equal(o2, twin.obs.cpu().numpy())
             assert np.array_equal(o2[..., 12:], obs[..., 12:])
         if t == 50:
             o3 = sim.reset_host()
-            assert np.array_equal(o3, sim.obs.cpu().numpy())
-    sim.close()
+            twin.reset()
+            assert np.array_equal(o3, sim.obs.cpu().numpy()) and np.array_equal(o3, twin.obs.cpu().numpy())
+    sim.close(); twin.close()
 
 
 def test_cuda_host_mirror_tracks_the_oracle():
@@ -219,8 +227,10 @@ def test_cuda_per_cta_sequencing_is_bit_identical_to_serial_launches(shape, monk
         st = sim.get_state()
         outs.append([x.clone() for x in st] + [sim.obs.clone(), sim.reward.clone(), sim.truncated.clone()] +
                     ([torch.from_numpy(sim.episode_stats())] if ar else []))
+    def bits(x):        # NaN-proof bit comparison (a DYN drone has no ground: diverged envs hold inf/NaN in both runs alike)
+        return x.contiguous().view(torch.int64 if x.element_size() == 8 else (torch.int32 if x.element_size() == 4 else torch.uint8))
     for x, y in zip(*outs):
-        assert torch.equal(x, y)
+        assert torch.equal(bits(x), bits(y))
     fast.close(); slow.close()
 
 
@@ -341,3 +351,52 @@ print("rank", rank, "ok")
     assert torch.equal(outs[0], outs[1])
     for env in envs:
         env.close()
+
+
+@pytest.mark.parametrize("act,flags,precision,freq,E", [("rpm", 0, "f32", 30, 1000), ("rpm", 0, "f64", 48, 333), ("rpm", 3, "f32", 30, 1000),
+                                                         ("rpm", 3, "f64", 30, 200), ("vel", 0, "f32", 48, 777), ("vel", 2, "f64", 48, 130),
+                                                         ("rpm", 0, "f32", 240, 4096)])
+def test_cuda_bulk_copy_path_is_bit_identical_to_the_per_thread_path(act, flags, precision, freq, E, monkeypatch):
+    """Single-drone RL envs with 4-wide actions run the bulk-copy data path (gpd_step_bulk.cuh) by default.  Against the
+    per-thread / TMA-box kernel (GPD_BULK=0): identical bits in state, observation, reward, flags, terminal rows and episode
+    statistics, with ragged last tiles, per-env initial poses, auto-reset, force models and the in-loop controller; also
+    for a first step without a previous observation and through a masked reset."""
+    rng = np.random.default_rng(12)
+    kw = _kw("hover", act, 1, freq, flags, model=DroneModel.CF2P if act == "vel" else DroneModel.CF2X)
+    xyz = rng.uniform([-1, -1, 0.2], [1, 1, 1.5], size=(E, 1, 3))
+    rpy = rng.uniform(-0.2, 0.2, size=(E, 1, 3))
+    kw["init_xyz"], kw["init_rpy"] = xyz, rpy
+    bulk = make_sim(kw, E, precision, auto_reset=True)
+    monkeypatch.setenv("GPD_BULK", "0")
+    ref = make_sim(kw, E, precision, auto_reset=True)
+    monkeypatch.delenv("GPD_BULK")
+
+    def bits(x):
+        return x.contiguous().view(torch.int64 if x.element_size() == 8 else (torch.int32 if x.element_size() == 4 else torch.uint8))
+
+    def same(tag):
+        for u, v in zip(bulk.get_state(), ref.get_state()):
+            assert torch.equal(bits(u), bits(v)), tag
+    # a first step with NO previous observation (all-zero ring), then the regular chain
+    a0 = torch.from_numpy(rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)).cuda()
+    for sim in (bulk, ref):
+        sim._have_prev = False
+    ob, oref = bulk.step(a0), ref.step(a0)
+    for u, v in zip(ob, oref):
+        assert torch.equal(bits(u), bits(v))
+    same("first step")
+    for t in range(40):
+        a = torch.from_numpy(rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)).cuda()
+        ob, oref = bulk.step(a), ref.step(a)
+        for u, v in zip(ob, oref):
+            assert torch.equal(bits(u), bits(v)), t
+        assert torch.equal(bits(bulk.terminal_kin), bits(ref.terminal_kin)), t
+        if t % 13 == 5:
+            same(t)
+        if t == 20:
+            m = torch.from_numpy((rng.random(E) < 0.3).astype(np.uint8)).cuda()
+            assert torch.equal(bits(bulk.reset(m)), bits(ref.reset(m)))
+    same("end")
+    sb, sr = bulk.episode_stats(), ref.episode_stats()
+    assert sb[0] > 0 and np.array_equal(sb, sr)
+    bulk.close(); ref.close()
