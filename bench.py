@@ -263,16 +263,22 @@ class Timer:
     def __init__(self, torch, dist, world, dev):
         self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
 
-    def window(self, fn, sleep_cycles=400_000):
+    def window(self, fn, sleep_cycles=400_000, events=None):
+        """`events`: a pair of external events that `fn`'s CUDA graph records itself, as its first and last node (the window
+        then starts when the device starts the graph, not when the host asked for it)."""
         torch = self.torch
         if self.world > 1:
             self.dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda._sleep(sleep_cycles)
-        e0.record()
-        fn()
-        e1.record()
+        if events is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+        else:
+            e0, e1 = events
+            fn()
         torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier()
@@ -457,18 +463,18 @@ def b200_arm(a):
     torch.cuda.synchronize()
     K = max(1, a.steps)
     # EXACTLY K steps per timed window.  Three launch modes (--launch auto picks by K):
-    #   direct  K <= 256: K plain stream launches enqueued while the device sleeps (Timer.window), so none of the host launch
-    #           cost and no graph-launch latency (~8 us per graph, measured) falls between the events; consecutive step kernels
-    #           overlap through programmatic dependent launch exactly as they do in a rollout loop
-    #   single  K <= 1024: ONE graph of K kernel nodes.  The observation ping-pong and the set rotation repeat every `period`
-    #           steps, so m = period / gcd(K, period) such graphs are captured back to back and replayed round-robin: every
-    #           replay continues the simulation exactly where the previous one stopped
+    #   single  K <= 1024 (default): ONE graph = [event record, K step kernels, event record].  The two CUDA events are nodes of
+    #           the graph, so the window is the device time of exactly the K steps — the ~8 us the device needs to start a
+    #           graph (measured, profiles/r02) is launch latency, not step time, and stays outside.  The observation ping-pong
+    #           and the set rotation repeat every `period` steps, so m = period / gcd(K, period) such graphs are captured back
+    #           to back and replayed round-robin: every replay continues the simulation exactly where the previous one stopped
+    #   direct  K plain stream launches enqueued while the device sleeps (Timer.window), events recorded on the stream
     #   cycles  longer runs: `reps` replays of a 128-step graph + a tail graph inside the window and, outside it, the complement
     #           that completes the tail's cycle
     from math import gcd
     mode = a.launch
     if mode == "auto":
-        mode = "direct" if K <= 256 else ("single" if K <= 1024 else "cycles")
+        mode = "single" if K <= 1024 else "cycles"
     if a.no_graph:
         mode = "direct"
     gper = period * 8
@@ -479,7 +485,15 @@ def b200_arm(a):
     if mode != "direct":
         try:
             if mode == "single":
-                graphs = [graph_of(torch, (lambda i=i: run_steps(K, k0=i * K))) for i in range(m)]
+                # the two timing events are the first and the last node of each graph (external events: real record nodes)
+                gev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                       for _ in range(m)]
+
+                def unit(i):
+                    gev[i][0].record()
+                    run_steps(K, k0=i * K)
+                    gev[i][1].record()
+                graphs = [graph_of(torch, (lambda i=i: unit(i))) for i in range(m)]
             else:
                 graphs = {"main": graph_of(torch, lambda: run_steps(gper)),
                           "tail": graph_of(torch, lambda: run_steps(tail)) if tail else None,
@@ -528,7 +542,7 @@ def b200_arm(a):
     # long enough for the host to enqueue the whole window behind it (direct mode: ~10 us of host time per launch)
     sleep_cycles = 400_000 + (40_000 * K if mode == "direct" else 60 * min(K, 4096))
     for _ in range(trials):
-        ms_local = timer.window(timed_unit, sleep_cycles)
+        ms_local = timer.window(timed_unit, sleep_cycles, events=gev[nxt[0]] if mode == "single" else None)
         after_unit()
         ms_max, per = timer.max_over_ranks(ms_local)
         windows.append(ms_max)
@@ -685,7 +699,8 @@ def b200_arm(a):
             launch = (f"{K} direct stream launches per timed window, enqueued behind a device-side sleep"
                       + (f" (graph capture failed: {graph_error})" if graph_error else ""))
         elif mode == "single":
-            launch = f"ONE CUDA graph of {K} step kernels per timed window ({m} such graphs replayed round-robin)"
+            launch = (f"ONE CUDA graph per timed window: [event record, {K} step kernels, event record] "
+                      f"({m} such graphs replayed round-robin)")
         else:
             launch = "CUDA graph of %d step kernels x %d replays + %d-step tail graph" % (gper, reps, tail)
         line = {
@@ -696,7 +711,9 @@ def b200_arm(a):
                                   l2=f"rotating {nsets} env sets per GPU (~{nsets * E * 700 / 1e6:.0f} MB touched per cycle > 126 MB L2)",
                                   launch=launch, streams=nstreams,
                                   timing=f"median of {trials} windows of exactly {K} steps, each behind a device-side sleep and "
-                                         "bracketed by barrier + synchronize; CUDA events; max over ranks"),
+                                         "bracketed by barrier + synchronize; CUDA events"
+                                         + (" recorded by the graph itself (first and last node)" if mode == "single" else "")
+                                         + "; max over ranks"),
             "trials_ms": windows,
             "rank_ms": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "per_rank": per_rank},
             "clocks": clocks,

@@ -685,7 +685,7 @@ int gpd_step(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_ou
 }
 
 // ---- host-buffer paths -------------------------------------------------------------------------------------------------
-struct HostSizes { size_t rs, act_b, obs_b, obs_pad, pack_b, E; };
+struct HostSizes { size_t rs, act_b, obs_b, obs_pad, pack_b, E, rew_pad, flag_pad; };
 static HostSizes host_sizes(const gpd_sim* s)
 {
     HostSizes z;
@@ -696,6 +696,8 @@ static HostSizes host_sizes(const gpd_sim* s)
     z.E = (size_t)s->cfg.num_envs;
     z.obs_pad = (z.obs_b + 15) & ~size_t(15);     // keeps the reward block aligned for Real stores
     z.pack_b = z.obs_pad + z.E * z.rs + 2 * z.E;
+    z.rew_pad = (z.E * z.rs + 15) & ~size_t(15);  // mirror staging: reward | terminated | truncated, each 16-byte aligned
+    z.flag_pad = (z.E + 15) & ~size_t(15);
     return z;
 }
 
@@ -708,8 +710,8 @@ static int ensure_host_path(gpd_sim* s)
     // laid out the same way (the Python facade allocates them so) the whole result travels in ONE device-to-host copy
     void *act = nullptr, *o0 = nullptr, *o1 = nullptr, *tk = nullptr, *mk = nullptr;
     cudaError_t e = cudaMalloc(&act, z.act_b);
-    if (e == cudaSuccess) e = cudaMalloc(&o0, z.pack_b);
-    if (e == cudaSuccess) e = cudaMalloc(&o1, z.pack_b);
+    if (e == cudaSuccess) e = cudaMalloc(&o0, z.pack_b + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&o1, z.pack_b + 64);
     if (e == cudaSuccess) e = cudaMalloc(&tk, (size_t)s->D * 12 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&mk, z.E);
     if (e == cudaSuccess) e = cudaMemset(tk, 0, (size_t)s->D * 12 * sizeof(float));
@@ -923,8 +925,9 @@ int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_pre
     }
     char* pack = (char*)s->h_obs[nxt] + z.obs_pad;    // reward / flags staging lives behind the internal observation slot
     void* d_rew = pack;
-    uint8_t* d_term = (uint8_t*)(pack + z.E * z.rs);
-    uint8_t* d_trunc = d_term + z.E;
+    const bool tight = z.rew_pad == z.E * z.rs && z.flag_pad == z.E;     // E % 16 == 0: the staging is [reward|term|trunc] packed
+    uint8_t* d_term = (uint8_t*)(pack + z.rew_pad);
+    uint8_t* d_trunc = d_term + z.flag_pad;
     if (m.chunks <= 1) {
         CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
         int rc = step_impl(s, s->h_act, d_obs_prev, d_obs_out, d_rew, d_term, d_trunc, terminal_kin ? s->h_tkin : nullptr, m.d_kin_t, stream);
@@ -955,7 +958,7 @@ int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_pre
     }
     if (internal) { s->h_cur = nxt; s->h_has_prev = true; }
     // reward and flags of every env (one packed copy when the caller's arrays are laid out like the staging)
-    const bool packed = reward && (void*)terminated == (char*)reward + z.E * z.rs && truncated == terminated + z.E;
+    const bool packed = tight && reward && (void*)terminated == (char*)reward + z.E * z.rs && truncated == terminated + z.E;
     if (packed) {
         CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs + 2 * z.E, cudaMemcpyDeviceToHost, st));
     } else {
