@@ -533,10 +533,15 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         const size_t rs = f64 ? 8 : 4;
         const size_t bsm = (size_t)DPB * s->W * 4 + 3 * (size_t)DPB * 4 * rs + (size_t)DPB * 16 + 2 * (size_t)DPB * rs +
                            2 * (size_t)DPB * 4 + 2 * (size_t)DPB + 8 * 32;
+        // Eligible: single-drone RL env, 4-wide actions, whole-float4 rows, 16-row-aligned tiles that fit shared memory.
+        // Default on for rows of at most 320 bytes (30 Hz: W = 72): measured 9.2 -> 8.6 us (FP32), 16.1 -> 13.4 us (FP64) at
+        // 65,536 envs and 131 -> 121 us at 1 M envs; at 48 Hz (W = 108, 33 KB tiles, 6 CTAs per SM) the TMA-box kernel is
+        // ahead (11.4 vs 12.3 us).  GPD_BULK=1 forces it where eligible, GPD_BULK=0 turns it off.
         const char* ev = getenv("GPD_BULK");
-        s->bulk_ok = !(ev && atoi(ev) == 0) && !ctrl && N == 1 && A == 4 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 &&
-                     bsm <= (size_t)smem_optin &&
-                     (cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_VEL);
+        const bool eligible = !ctrl && N == 1 && A == 4 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 &&
+                              bsm <= (size_t)smem_optin &&
+                              (cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_VEL);
+        s->bulk_ok = eligible && (ev ? atoi(ev) != 0 : s->W * 4 <= 320);
         s->lc_bulk.threads = DPB; s->lc_bulk.grid = L.grid; s->lc_bulk.smem = bsm; s->lc_bulk.pdl = 0;
     }
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
