@@ -56,63 +56,16 @@ struct BulkSmem {
     __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4 * 8); }      // up to 8 warps
 };
 
+// One thread's share of a tile: state / action / counters from shared memory, the arithmetic of gpd::step_kernel, results
+// back into the tile (plus the few per-drone extras that live only in global memory).  `sub` = timeline slot or -1.
 template <typename R, int KIND>
-// registers: FP32 lean 64 (8 CTAs of 128 threads), DSLPID 72, force models 80; FP64 128 — shared memory (26-53 KB per tile)
-// caps the FP64 variants at 512 threads per SM anyway, so they get the registers that would otherwise spill
-__global__ void __launch_bounds__(128, sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 8 : (KIND == GPD_K_PID ? 7 : 5)) : 4)
-step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
+__device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const BulkSmem<R>& sm, int t, int64_t row0, int rows, int tl)
 {
     constexpr bool LEAN = KIND == GPD_K_LEAN, HAS_PID = KIND == GPD_K_PID;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    const int t = threadIdx.x;
-    const int bid = (int)blockIdx.x + a.cta0;
-    const int T = a.DPB;
-    BulkSmem<R> sm{ smem_raw, T, a.W };
-    const int64_t row0 = (int64_t)bid * T;
-    const int64_t d = row0 + t;             // N == 1: drone = env
-    const bool active = d < a.D;
-    const int rows = (int)min((int64_t)T, a.D - row0);
-    const bool full = rows == T;
     const DevDrone<R>& P = a.drone;
-
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();
-    if (t == 0) mbar_init(&bar, 1);
-    if (a.tile_dep) {
-        if (t == 0) {
-            uint32_t* seq = a.tile_seq + (int64_t)bid * 8;
-            const uint32_t done0 = ld_acquire_gpu(seq + 1);
-            const uint32_t mine = atomicAdd(seq, 1u);
-            if (done0 != mine)
-                while (ld_acquire_gpu(seq + 1) != mine) __nanosleep(32);
-        }
-        __syncthreads();
-        if (a.pdl_trigger_early) pdl_launch_dependents();
-    } else {
-        if (a.pdl_trigger_early) pdl_launch_dependents();
-        __syncthreads();
-        pdl_wait();
-    }
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 1] = gtime();
-
-    // ---- loads: everything this tile needs, in flight at once ----
-    if (t == 0) {
-        fence_proxy_async_global();         // generic-proxy writes of the tile's previous step (ragged tails) -> bulk reads
-        const uint32_t v4b = (uint32_t)sizeof(V4<R>);
-        // the last tile of the buffer must not read past its end: its final row loses the 16 stray bytes
-        const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((row0 + rows >= a.D) ? 16u : 0u) : 0u;
-        const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
-        const uint32_t total = ob + 3 * st + (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u);
-        mbar_expect_tx(&bar, total);
-        if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + a.A, ob, &bar);
-        bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
-        bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
-        bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
-        bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
-        bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);                  // library arrays are padded to whole tiles
-        bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
-        if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
-    }
+    const int64_t d = row0 + t;             // N == 1: drone = env
+    const bool active = t < rows;
+    const bool full = rows == sm.T;
     // what does not come through shared memory: per-index constants and the optional per-drone extras
     V4<R> tg = M<R>::make4(R(0), R(0), R(0), R(0)), ip0 = tg, iq0 = tg;
     R rpm_prev[4] = { R(0), R(0), R(0), R(0) };
@@ -127,13 +80,6 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
             }
         }
     }
-    if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
-        float* r = sm.obs() + (size_t)t * a.W;
-        for (int k = 12; k < a.W; ++k) r[k] = 0.f;
-    }
-    mbar_wait(&bar, 0);
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
-
     State<R> s;
     s.px = s.py = s.pz = s.qx = s.qy = s.qz = R(0); s.qw = R(1);
     s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
@@ -211,7 +157,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
             dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, last, avx, avy, avz);
         }
     }
-    if (a.timeline && t == 0 && s.px == s.px) a.timeline[(int64_t)bid * 8 + 3] = gtime();
+    if (a.timeline && tl >= 0 && t == 0 && s.px == s.px) a.timeline[(int64_t)tl * 8 + 3] = gtime();
 
     // ---- _updateAndStoreKinematicInformation (BaseAviary.py:374,509-519) + outputs ----
     R roll, pitch, yaw;
@@ -322,6 +268,99 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
             for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.D + d] = kin[k];
         }
     }
+}
+
+// thread 0 of the physics group: combine the warps' statistics partials of one tile, RED into the tile's slot
+template <typename R>
+__device__ __forceinline__ void bulk_tile_stats(const StepArgs<R>& a, const BulkSmem<R>& sm, int64_t tile, int rows)
+{
+    const int T = sm.T;
+    {
+        if (a.auto_reset) {
+            StatSlot* slot = a.p.stat_slots + tile;
+            int n = 0, len = 0, mn = 0x7fffffff, mx = (int)0x80000000;
+            float sr = 0.f, sr2 = 0.f, stt = 0.f;
+            for (int w = 0; w < ((T + 31) >> 5); ++w) {
+                const float* sf = sm.stat_f() + 4 * w;
+                const int* si = sm.stat_i() + 4 * w;
+                n += si[0]; len += si[1]; mn = min(mn, si[2]); mx = max(mx, si[3]);
+                sr += sf[0]; sr2 += sf[1]; stt += sf[2];
+            }
+            if (n > 0) {
+                atomicAdd(&slot->s[0], (double)n);
+                atomicAdd(&slot->s[1], (double)sr);
+                atomicAdd(&slot->s[2], (double)len);
+                atomicAdd(&slot->s[3], (double)sr2);
+                atomicMin(&slot->mn, mn);
+                atomicMax(&slot->mx, mx);
+                if (stt > 0.f) atomicAdd(&slot->s[5], (double)stt);
+            }
+            atomicAdd(&slot->s[4], (double)rows);
+        }
+    }
+}
+
+template <typename R, int KIND>
+// registers: FP32 lean 64 (8 CTAs of 128 threads), DSLPID 72, force models 80; FP64 128 — shared memory (26-53 KB per tile)
+// caps the FP64 variants at 512 threads per SM anyway, so they get the registers that would otherwise spill
+__global__ void __launch_bounds__(128, sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 8 : (KIND == GPD_K_PID ? 7 : 5)) : 4)
+step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const int t = threadIdx.x;
+    const int bid = (int)blockIdx.x + a.cta0;
+    const int T = a.DPB;
+    BulkSmem<R> sm{ smem_raw, T, a.W };
+    const int64_t row0 = (int64_t)bid * T;
+    const int rows = (int)min((int64_t)T, a.D - row0);
+    const bool full = rows == T;
+
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();
+    if (t == 0) mbar_init(&bar, 1);
+    if (a.tile_dep) {
+        if (t == 0) {
+            uint32_t* seq = a.tile_seq + (int64_t)bid * 8;
+            const uint32_t done0 = ld_acquire_gpu(seq + 1);
+            const uint32_t mine = atomicAdd(seq, 1u);
+            if (done0 != mine)
+                while (ld_acquire_gpu(seq + 1) != mine) __nanosleep(32);
+        }
+        __syncthreads();
+        if (a.pdl_trigger_early) pdl_launch_dependents();
+    } else {
+        if (a.pdl_trigger_early) pdl_launch_dependents();
+        __syncthreads();
+        pdl_wait();
+    }
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 1] = gtime();
+
+    // ---- loads: everything this tile needs, in flight at once ----
+    if (t == 0) {
+        fence_proxy_async_global();         // generic-proxy writes of the tile's previous step (ragged tails) -> bulk reads
+        const uint32_t v4b = (uint32_t)sizeof(V4<R>);
+        // the last tile of the buffer must not read past its end: its final row loses the 16 stray bytes
+        const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((row0 + rows >= a.D) ? 16u : 0u) : 0u;
+        const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
+        const uint32_t total = ob + 3 * st + (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u);
+        mbar_expect_tx(&bar, total);
+        if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + a.A, ob, &bar);
+        bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
+        bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
+        bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
+        bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
+        bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);                  // library arrays are padded to whole tiles
+        bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
+        if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
+    }
+    if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
+        float* r = sm.obs() + (size_t)t * a.W;
+        for (int k = 12; k < a.W; ++k) r[k] = 0.f;
+    }
+    mbar_wait(&bar, 0);
+    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
+
+    bulk_tile_physics<R, KIND>(a, sm, t, row0, rows, bid);
     fence_proxy_async_smem();               // this thread's shared-memory writes -> the bulk stores below
     __syncthreads();
     if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();
@@ -342,27 +381,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
             if (a.truncated) bulk_s2g(a.truncated + row0, sm.trunc(), (uint32_t)T);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (a.auto_reset) {                 // combine the warps' partials while the stores drain
-            StatSlot* slot = a.p.stat_slots + bid;
-            int n = 0, len = 0, mn = 0x7fffffff, mx = (int)0x80000000;
-            float sr = 0.f, sr2 = 0.f, stt = 0.f;
-            for (int w = 0; w < ((T + 31) >> 5); ++w) {
-                const float* sf = sm.stat_f() + 4 * w;
-                const int* si = sm.stat_i() + 4 * w;
-                n += si[0]; len += si[1]; mn = min(mn, si[2]); mx = max(mx, si[3]);
-                sr += sf[0]; sr2 += sf[1]; stt += sf[2];
-            }
-            if (n > 0) {
-                atomicAdd(&slot->s[0], (double)n);
-                atomicAdd(&slot->s[1], (double)sr);
-                atomicAdd(&slot->s[2], (double)len);
-                atomicAdd(&slot->s[3], (double)sr2);
-                atomicMin(&slot->mn, mn);
-                atomicMax(&slot->mx, mx);
-                if (stt > 0.f) atomicAdd(&slot->s[5], (double)stt);
-            }
-            atomicAdd(&slot->s[4], (double)rows);
-        }
+        bulk_tile_stats<R>(a, sm, bid, rows);
         if (a.tile_dep) {
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
             red_release_gpu_inc(a.tile_seq + (int64_t)bid * 8 + 1);
@@ -374,5 +393,6 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     if (!a.pdl_trigger_early) pdl_launch_dependents();
     if (a.tile_dep) pdl_wait();             // keep stream order transitive (see gpd::step_kernel)
 }
+
 
 }  // namespace gpd
