@@ -76,7 +76,9 @@ def config_dict(a, world, **extra):
     """Same keys on both arms (the driver compares the dicts)."""
     S = 240 // a.ctrl_freq
     c = {"workload": workload_name(a), "envs_per_gpu": a.envs, "substeps_per_step": S,
-         "parallelism": f"env-sharded x{world}, no data-path collective"}
+         "parallelism": f"env-sharded x{world}, no data-path collective",
+         "l2": (f"GPU arm: {a.sets} independent env sets per GPU stepped in rotation (~{a.sets * a.envs * 700 / 1e6:.0f} MB touched per "
+                "cycle > 126 MB L2), so every step's inputs were last touched a whole cycle ago; CPU arm: not applicable")}
     c.update(extra)
     return c
 
@@ -311,6 +313,7 @@ def measure_config(torch, timer, make_env, make_action, nsets, steps, trials=3):
     acts = [make_action(envs[0], k) for k in range(2 * nsets)]
     for e in envs:
         e.reset()
+        e._sim.set_step_chaining(True)      # pre-generated actions (see b200_arm)
     period = 2 * nsets
     steps = max(period, (steps // period) * period)
 
@@ -430,6 +433,10 @@ def b200_arm(a):
     acts = [(torch.rand((E, 1, 4), generator=g, device=dev) * 2 - 1) for _ in range(2 * nsets)]
     for e in envs:
         e.reset()
+        # the K timed steps are launched back to back from action buffers generated long before: chained stepping is valid
+        # (gpd_set_step_chaining): consecutive launches overlap across the kernel boundary, each tile ordered behind its own
+        # previous step.  A policy-in-the-loop rollout (rollout.py) does not chain.
+        e._sim.set_step_chaining(True)
     period = 2 * nsets
 
     nstreams = max(1, min(a.streams, nsets))
@@ -676,7 +683,7 @@ def b200_arm(a):
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_note": (tr or {}).get("note"),
                 "traffic_steady_state": ((tr or {}).get("steady_state_bytes_per_env_step") or 0) * E or None,
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel<%s,LEAN,N=1,VEC>" % ("double" if a.precision == "f64" else "float"),
+                "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel_bulk<%s,LEAN>" % ("double" if a.precision == "f64" else "float"),
                 "kernel_ms_per_launch": per_launch_ms,
                 "note": "consecutive launches overlap across the kernel boundary (programmatic dependent launch + per-CTA step "
                         "sequencing): kernel_ms_per_launch is the steady-state time per launch on ONE stream, not one launch's span"}
@@ -707,13 +714,13 @@ def b200_arm(a):
             "metric": METRIC, "value": value, "unit": "drone-substeps/s", "n_gpus": world, "steps": K, "warmup": wu,
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic",
-            "config": config_dict(a, world,
-                                  l2=f"rotating {nsets} env sets per GPU (~{nsets * E * 700 / 1e6:.0f} MB touched per cycle > 126 MB L2)",
-                                  launch=launch, streams=nstreams,
-                                  timing=f"median of {trials} windows of exactly {K} steps, each behind a device-side sleep and "
-                                         "bracketed by barrier + synchronize; CUDA events"
-                                         + (" recorded by the graph itself (first and last node)" if mode == "single" else "")
-                                         + "; max over ranks"),
+            "config": config_dict(a, world),        # the same dict on both arms (the driver compares them)
+            "measurement": {
+                "launch": launch, "streams": nstreams,
+                "timing": f"median of {trials} windows of exactly {K} steps, each behind a device-side sleep and "
+                          "bracketed by barrier + synchronize; CUDA events"
+                          + (" recorded by the graph itself (first and last node)" if mode == "single" else "")
+                          + "; max over ranks"},
             "trials_ms": windows,
             "rank_ms": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "per_rank": per_rank},
             "clocks": clocks,

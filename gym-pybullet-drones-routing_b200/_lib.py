@@ -31,6 +31,7 @@ SYMBOLS = [
     "gpd_set_timeline_buffer", "gpd_count_nonfinite", "gpd_set_targets", "gpd_mirror_alloc", "gpd_mirror_free",
     "gpd_mirror_attach", "gpd_mirror_row", "gpd_step_mirror", "gpd_step_mirror_begin", "gpd_step_mirror_end",
     "gpd_reset_mirror", "gpd_nccl_unique_id", "gpd_nccl_comm_init", "gpd_nccl_comm_destroy", "gpd_adjacency",
+    "gpd_set_step_chaining",
 ]
 
 
@@ -141,6 +142,7 @@ def load(path: str | None = None):
     L.gpd_set_init_poses.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.c_int]
     L.gpd_reset.argtypes = [vp, u8p, vp, vp, vp]
     L.gpd_step.argtypes = [vp, vp, vp, vp, vp, u8p, u8p, vp, vp]
+    L.gpd_set_step_chaining.argtypes = [vp, C.c_int]
     L.gpd_step_host.argtypes = [vp, vp, vp, vp, u8p, u8p, vp, vp]
     L.gpd_reset_host.argtypes = [vp, u8p, vp, vp]
     L.gpd_get_state.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <unordered_map>
 #include <vector>
@@ -95,8 +96,10 @@ struct gpd_sim {
     int dpb = 0;
     int copy_threads = 0;
     int tile_dep = 1;                 // per-CTA step sequencing (decided in gpd_create from the number of waves)
+    int chaining = 0;                 // gpd_set_step_chaining: the caller vouches for its step inputs (see gpd.h)
     bool bulk_ok = false;             // single-drone RL env with 4-wide actions: the bulk-copy data path (gpd_step_bulk.cuh)
     LaunchCfg lc_bulk{};
+    int bulk_direct = 0;              // BulkSmem::direct
     int64_t d_pad = 0;                // per-env scalar arrays are allocated for whole tiles (grid * DPB entries)
     const void* last_obs = nullptr;   // the observation buffer most recently written by gpd_step / gpd_reset (device)
     uint64_t obs_seq = 0;             // bumped whenever the device observation chain advances (or is replaced by the caller)
@@ -163,6 +166,28 @@ static cudaError_t use_device(int dev)
     cudaError_t e = cudaGetDevice(&cur);
     if (e != cudaSuccess) return e;
     return cur == dev ? cudaSuccess : cudaSetDevice(dev);
+}
+
+// Chained stepping (gpd_set_step_chaining): a step kernel is launched programmatically only behind ANOTHER step kernel of
+// this library on the same stream (of any handle: independent env sets stepped in rotation chain too).  The library tracks
+// per (device, stream) whether its last launch there was a step kernel; every other launch it makes (reset, set/get state,
+// statistics, ...) breaks the chain, so the step that follows is fully ordered behind it.  Work enqueued by others is the
+// caller's side of the contract.
+struct ChainTable {
+    std::mutex mu;
+    std::unordered_map<unsigned long long, bool> last_was_step;
+    static unsigned long long key(int dev, cudaStream_t st) { return ((unsigned long long)(uintptr_t)st << 6) ^ (unsigned long long)dev; }
+    bool get(int dev, cudaStream_t st) { std::lock_guard<std::mutex> l(mu); auto it = last_was_step.find(key(dev, st)); return it != last_was_step.end() && it->second; }
+    void set(int dev, cudaStream_t st, bool v) { std::lock_guard<std::mutex> l(mu); last_was_step[key(dev, st)] = v; }
+    void clear() { std::lock_guard<std::mutex> l(mu); last_was_step.clear(); }
+};
+static ChainTable g_chain;
+// a launch on `st` that is not a step kernel; calls without a stream of their own (synchronous uploads) break every chain
+static inline void unchain(gpd_sim* s, void* stream = nullptr, bool all = false)
+{
+    if (!s) return;
+    if (all) g_chain.clear();
+    else g_chain.set(s->cfg.device, (cudaStream_t)stream, false);
 }
 
 static int action_width(int act)
@@ -343,9 +368,9 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
         a.p.ep_ret = er; a.p.stat_slots = slots;
     }
     if ((rc = upload_targets(s, a, s->target_host.data(), 0))) return rc;
-    {   // per-CTA step sequencing (see ld_acquire_gpu in gpd_kernels.cuh): one 32-byte slot per CTA
-        uint32_t* seq = nullptr;
-        if ((rc = dev_alloc(s, &seq, (size_t)s->lc.grid * 8))) return rc;
+    {   // per-CTA step sequencing (see tile_claim_and_wait in gpd_kernels.cuh): one 64-bit word per CTA at a 32-byte stride
+        unsigned long long* seq = nullptr;
+        if ((rc = dev_alloc(s, &seq, (size_t)s->lc.grid * 4))) return rc;
         a.tile_seq = seq;
         a.tile_dep = s->tile_dep;
     }
@@ -363,6 +388,8 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
         a.skip_aux = (sizeof(R) == 4 && rpm_act && c.physics_flags == 0 && c.env_kind != GPD_ENV_CTRL && !(ev && atoi(ev))) ? 1 : 0;
     }
     a.tma_edge_bytes = s->tma_edge_bytes;
+    a.bulk_direct = s->bulk_direct;
+    a.dbg = getenv("GPD_DEBUG_UNSAFE") ? atoi(getenv("GPD_DEBUG_UNSAFE")) : 0;
     a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207
@@ -531,17 +558,24 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     s->d_pad = s->lc.grid * (int64_t)DPB;
     {   // bulk-copy data path: same tiles (DPB envs per CTA), T threads, everything staged in shared memory
         const size_t rs = f64 ? 8 : 4;
-        const size_t bsm = (size_t)DPB * s->W * 4 + 3 * (size_t)DPB * 4 * rs + (size_t)DPB * 16 + 2 * (size_t)DPB * rs +
-                           2 * (size_t)DPB * 4 + 2 * (size_t)DPB + 8 * 32;
+        // what bypasses shared memory (BulkSmem in gpd_step_bulk.cuh): shared memory per env bounds the tiles in flight per SM
+        // measured (profiles/r02, 65,536 envs, FP32, 200-step windows): 8.95 / 8.77 / 8.62 us for direct = 0 / 1 / 2
+        // (FP64 13.74 -> 13.31 us; 1 M envs unchanged within noise): default 2
+        int direct = 2;
+        if (const char* dv = getenv("GPD_BULK_DIRECT")) direct = atoi(dv) < 0 ? 0 : (atoi(dv) > 2 ? 2 : atoi(dv));
+        s->bulk_direct = direct;
+        const size_t bsm = (size_t)DPB * s->W * 4 + (direct >= 2 ? 0 : 3 * (size_t)DPB * 4 * rs) +
+                           (direct ? 0 : (size_t)DPB * 16 + 2 * (size_t)DPB * rs + 2 * (size_t)DPB * 4 + 2 * (size_t)DPB) + 8 * 32;
         // Eligible: single-drone RL env, 4-wide actions, whole-float4 rows, 16-row-aligned tiles that fit shared memory.
-        // Default on for rows of at most 320 bytes (30 Hz: W = 72): measured 9.2 -> 8.6 us (FP32), 16.1 -> 13.4 us (FP64) at
-        // 65,536 envs and 131 -> 121 us at 1 M envs; at 48 Hz (W = 108, 33 KB tiles, 6 CTAs per SM) the TMA-box kernel is
-        // ahead (11.4 vs 12.3 us).  GPD_BULK=1 forces it where eligible, GPD_BULK=0 turns it off.
+        // Default on for rows of at most 512 bytes (30 Hz: W = 72, 48 Hz: W = 108): measured 9.2 -> 8.6 us (FP32),
+        // 16.1 -> 13.3 us (FP64) at 65,536 envs, 131 -> 121 us at 1 M envs, and at 48 Hz 11.35 -> 10.79 us once the state
+        // vectors bypass shared memory (direct = 2; with everything staged the TMA-box kernel was ahead there).  Longer rows
+        // (60 Hz and up) leave too few tiles per SM.  GPD_BULK=1 forces it where eligible, GPD_BULK=0 turns it off.
         const char* ev = getenv("GPD_BULK");
         const bool eligible = !ctrl && N == 1 && A == 4 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 &&
                               bsm <= (size_t)smem_optin &&
                               (cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_VEL);
-        s->bulk_ok = eligible && (ev ? atoi(ev) != 0 : s->W * 4 <= 320);
+        s->bulk_ok = eligible && (ev ? atoi(ev) != 0 : s->W * 4 <= 512);
         s->lc_bulk.threads = DPB; s->lc_bulk.grid = L.grid; s->lc_bulk.smem = bsm; s->lc_bulk.pdl = 0;
     }
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
@@ -610,6 +644,7 @@ int gpd_set_init_poses(gpd_sim* s, const double* xyz, const double* rpy, int per
 {
     if (!s || !xyz || !rpy) return fail(GPD_ERR_INVALID, "gpd_set_init_poses: null argument");
     CU(use_device(s->cfg.device));
+    unchain(s, nullptr, true);
     return s->cfg.precision == GPD_F64 ? upload_init(s, s->a64, xyz, rpy, per_env) : upload_init(s, s->a32, xyz, rpy, per_env);
 }
 
@@ -618,6 +653,7 @@ int gpd_set_targets(gpd_sim* s, const double* target_pos, int per_env)
     if (!s || !target_pos) return fail(GPD_ERR_INVALID, "gpd_set_targets: null argument");
     if (s->cfg.env_kind == GPD_ENV_CTRL) return fail(GPD_ERR_INVALID, "the Ctrl env has no target");
     CU(use_device(s->cfg.device));
+    unchain(s, nullptr, true);
     return s->cfg.precision == GPD_F64 ? upload_targets(s, s->a64, target_pos, per_env) : upload_targets(s, s->a32, target_pos, per_env);
 }
 
@@ -626,6 +662,7 @@ int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* o
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     if (obs_out && obs_out == obs_prev) return fail(GPD_ERR_INVALID, "obs_prev must not alias obs_out");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
@@ -655,24 +692,34 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         if (have && s->tma_edge) have = get_tmap(s, obs_prev, true, &te);
     }
     const int use_tma = have ? 1 : 0;
-    // the bulk copies need 16-byte aligned caller buffers (torch allocations are); anything else takes the per-thread path
-    const uintptr_t al = (uintptr_t)actions | (uintptr_t)obs_prev | (uintptr_t)obs_out | (uintptr_t)reward | (uintptr_t)terminated |
-                         (uintptr_t)truncated;
+    // the bulk copies need 16-byte aligned actions / observations (torch allocations and their rows are); anything else takes
+    // the per-thread kernel.  Reward / flag arrays that are not (rows of a [T][E] uint8 trajectory buffer) only switch those
+    // three outputs to plain stores: a sim keeps ONE kernel, so its FP32 results do not depend on the caller's buffer layout
+    // (the two kernels agree bit for bit in FP64; in FP32 only up to the compiler's FMA contraction choices).
+    const uintptr_t al = (uintptr_t)actions | (uintptr_t)obs_prev | (uintptr_t)obs_out;
+    const uintptr_t al_out = (uintptr_t)reward | (uintptr_t)terminated | (uintptr_t)truncated;
     const bool bulk = s->bulk_ok && (al & 15) == 0;
+    const int out_plain = (al_out & 15) != 0 ? 1 : 0;
     LaunchCfg lc = bulk ? s->lc_bulk : s->lc;
     if (ncta > 0) lc.grid = ncta;       // a sub-range of the CTAs (chunked host-mirror step); cta0 shifts the block index
+    if (s->tile_dep) {
+        // programmatic launch only when the caller opted in (gpd_set_step_chaining) and the library's previous launch on this
+        // stream was a step kernel; otherwise plain stream order (the kernel still claims / publishes its tiles, so a
+        // chained successor sequences correctly behind it)
+        lc.pdl = (s->chaining && lc.pdl && g_chain.get(s->cfg.device, st)) ? 1 : 0;
+    }
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        a.kin_t = kin_t; a.cta0 = (int32_t)cta0;
+        a.kin_t = kin_t; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
         if (bulk) CU(launch_step_bulk<double>(a, lc, st));
         else CU(launch_step<double>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     } else {
         StepArgs<float> a = s->a32;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        a.kin_t = kin_t; a.cta0 = (int32_t)cta0;
+        a.kin_t = kin_t; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
         if (bulk) CU(launch_step_bulk<float>(a, lc, st));
         else CU(launch_step<float>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     }
@@ -680,6 +727,14 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         s->last_obs = obs_out;
         ++s->obs_seq;
     }
+    g_chain.set(s->cfg.device, st, true);
+    return GPD_OK;
+}
+
+int gpd_set_step_chaining(gpd_sim* s, int enable)
+{
+    if (!s) return fail(GPD_ERR_INVALID, "null handle");
+    s->chaining = enable ? 1 : 0;
     return GPD_OK;
 }
 
@@ -822,10 +877,11 @@ int gpd_mirror_attach(gpd_sim* s, float* log, int64_t rows, int64_t row_len, int
     Mirror& m = s->mir;
     m.log = log; m.rows = rows; m.ld = row_len; m.col0 = col0;
     m.row = 0; m.valid = false; m.pending = false;
-    // Chunked issue: PCIe is full duplex and the copy engines run beside the SMs, so with the step cut into CTA sub-ranges the
-    // action upload of chunk c+1 overlaps the kernel of chunk c and the result download of chunk c-1 (measured: 141 -> ~90 us
-    // per 65,536-env step).  Worth it only when the copies dominate: >= 32,768 drones; GPD_MIRROR_CHUNKS overrides.
-    int chunks = s->D >= 32768 ? 4 : 1;
+    // Chunked issue (GPD_MIRROR_CHUNKS > 1): the step is cut into CTA sub-ranges on their own streams, so the action upload of
+    // chunk c+1 can overlap the kernel of chunk c and the result download of chunk c-1 (PCIe is full duplex).  Measured through
+    // the Python call site at 65,536 envs (profiles/r02): 139 / 147 / 166 / 193 us per step with 1 / 2 / 4 / 8 chunks — every
+    // chunk costs four more driver calls on the one host thread, which outweighs the overlap.  Default: one chunk.
+    int chunks = 1;
     if (const char* ev = getenv("GPD_MIRROR_CHUNKS")) chunks = atoi(ev);
     if (chunks > GPD_MIRROR_MAX_CHUNKS) chunks = GPD_MIRROR_MAX_CHUNKS;
     if (chunks > s->lc.grid) chunks = (int)s->lc.grid;
@@ -1041,6 +1097,7 @@ int gpd_get_state(gpd_sim* s, void* state20, void* rpy_rates, void* pid_state, i
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     if (s->cfg.precision == GPD_F64)
         CU(launch_get_state<double>(s->a64, (const float*)s->last_obs, (double*)state20, (double*)rpy_rates, (double*)pid_state, step_counter, (cudaStream_t)stream));
     else
@@ -1061,6 +1118,7 @@ int gpd_set_state(gpd_sim* s, const void* state20, const void* rpy_rates, const 
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     if (s->cfg.precision == GPD_F64)
         CU(launch_set_state<double>(s->a64, (const double*)state20, (const double*)rpy_rates, (const double*)pid_state, step_counter, (cudaStream_t)stream));
     else
@@ -1151,6 +1209,7 @@ int gpd_rollout_pid(gpd_sim* s, int32_t n_ctrl_steps, const void* waypoints, int
     if (s->cfg.drone.model == GPD_RACE) return fail(GPD_ERR_INVALID, "DSLPIDControl requires CF2X or CF2P");
     if (s->cfg.physics_flags & GPD_PHY_DW) return fail(GPD_ERR_INVALID, "gpd_rollout_pid does not support downwash");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     if (s->cfg.precision == GPD_F64)
         CU(launch_rollout_pid<double>(s->a64, n_ctrl_steps, (const double*)waypoints, n_wp, wp_counters, (double*)action, (cudaStream_t)stream));
     else
@@ -1162,6 +1221,7 @@ int gpd_count_nonfinite(gpd_sim* s, long long* out_host, void* stream)
 {
     if (!s || !out_host) return fail(GPD_ERR_INVALID, "gpd_count_nonfinite: null argument");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* cnt = (unsigned long long*)s->stats_out;       // reuse the 64-byte scratch
     CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
@@ -1253,6 +1313,7 @@ int gpd_episode_stats(gpd_sim* s, double out[8], int clear, void* nccl_comm, voi
     for (int k = 0; k < 8; ++k) out[k] = 0.0;
     if (!s->cfg.auto_reset) return fail(GPD_ERR_INVALID, "episode statistics are kept only with auto_reset");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     cudaStream_t st = (cudaStream_t)stream;
     StatSlot* slots = s->cfg.precision == GPD_F64 ? s->a64.p.stat_slots : s->a32.p.stat_slots;
     CU(launch_stats(slots, s->lc.grid, s->stats_out, clear, slots, st));
@@ -1284,6 +1345,7 @@ int gpd_adjacency(gpd_sim* s, double neighbourhood_radius, void* out, void* stre
 {
     if (!s || !out) return fail(GPD_ERR_INVALID, "gpd_adjacency: null argument");
     CU(use_device(s->cfg.device));
+    unchain(s, stream);
     if (s->cfg.precision == GPD_F64) CU(launch_adjacency<double>(s->a64, neighbourhood_radius, (double*)out, (cudaStream_t)stream));
     else CU(launch_adjacency<float>(s->a32, (float)neighbourhood_radius, (float*)out, (cudaStream_t)stream));
     return GPD_OK;

@@ -103,10 +103,13 @@ struct StepArgs {
     const uint8_t* reset_mask;   // reset kernel only
     unsigned long long* timeline; // diagnostics: [grid][8] phase timestamps (ns, %globaltimer) or nullptr
     float* kin_t;           // host-mirror export: feature-major copy [12][D] of the kinematic observation part, or nullptr
-    uint32_t* tile_seq;     // per-CTA step sequencing [grid][8]: word 0 = steps claimed, word 1 = steps completed (tile_dep)
+    unsigned long long* tile_seq;   // per-CTA step sequencing, one 64-bit word per tile at a 32-byte stride (tile_claim_and_wait)
     int32_t tile_dep;       // 1: a CTA waits only for ITS OWN tile's previous step (per-CTA flag) instead of the whole grid
     int32_t target_per_env; // 1: p.target holds D entries (per-env MultiHover targets), else N
     int32_t cta0;           // first CTA of this launch (0 unless the step is issued in chunks)
+    int32_t out_plain;      // bulk path, per call: reward / terminated / truncated are not all 16-byte aligned -> plain stores by the threads
+    int32_t dbg;            // EXPERIMENTS ONLY (GPD_DEBUG_UNSAFE): bit 0 = publish a tile without waiting for its stores, bit 1 = skip the claim
+    int32_t bulk_direct;    // bulk path: what bypasses shared memory (0 nothing, 1 the small per-env arrays, 2 the state vectors too)
     SimPtrs<R> p;
     DevDrone<R> drone;
     DevPid<R> pid;

@@ -32,19 +32,37 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Per-CTA step sequencing (tile_dep): CTA i of step k+1 depends only on CTA i of step k (same rows, same DPB), so instead
-// of the whole-grid griddepcontrol.wait it acquires its own tile's `completed` counter.  The step kernel is launched with
-// programmatic stream serialization and releases its dependents as soon as every CTA has CLAIMED its sequence number; a
-// dependent grid therefore starts only after every CTA of every earlier step kernel of the stream has started (and claimed),
-// which orders the claims and excludes deadlock: a spinning CTA only ever waits for a CTA that is already resident.
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+// of the whole-grid griddepcontrol.wait it waits for its own tile's previous step.  The step kernel is launched with
+// programmatic stream serialization and releases its dependents as soon as every CTA has CLAIMED its tile; a dependent
+// grid therefore starts only after every CTA of every earlier step kernel of the stream has started (and claimed), which
+// orders the claims and excludes deadlock: a spinning CTA only ever waits for a CTA that is already resident.
+//
+// One 64-bit word per tile, ONE L2 round trip at each end of a CTA's life:
+//     high 32 bits = steps claimed so far (wraps harmlessly: it falls off the top of the word)
+//     low  32 bits = steps claimed and not yet published (0 or 1 outside a transition, never more than the grids in flight)
+// claim   = atom.acquire.add (1 << 32) + 1: the old word tells this CTA its sequence number and, in the common case
+//           (pending == 0), that its predecessor has published — the acquire side makes the predecessor's tile visible;
+// publish = red.release.add -1 (borrows nothing: pending >= 1 while this CTA is alive).
+// A CTA that found predecessors pending polls until pending - 1 - (claims made after its own) == 0.
+__device__ __forceinline__ void tile_claim_and_wait(unsigned long long* w)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    unsigned long long old;
+    // acquire only: a claiming CTA has written nothing yet (an acq_rel atomic would put MEMBAR.ALL.GPU + ERRBAR in front, ~1 us)
+    asm volatile("atom.acquire.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(w), "l"(0x100000001ull) : "memory");
+    if ((uint32_t)old != 0u) {
+        const uint32_t mine = (uint32_t)(old >> 32);
+        for (;;) {
+            unsigned long long cur;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(w) : "memory");
+            const uint32_t later = (uint32_t)(cur >> 32) - mine - 1u;      // claims made after this one
+            if ((uint32_t)cur - 1u - later == 0u) break;
+            __nanosleep(32);
+        }
+    }
 }
-__device__ __forceinline__ void red_release_gpu_inc(uint32_t* p)
+__device__ __forceinline__ void tile_publish(unsigned long long* w)
 {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p) : "memory");
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(w), "l"(0xffffffffffffffffull) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
@@ -317,6 +335,65 @@ __device__ __forceinline__ void pid_action(const StepArgs<R>& a, int64_t d, cons
     for (int k = 0; k < 9; ++k) a.p.pid[(int64_t)k * a.D + d] = st[k];
 }
 
+// One substep of the ctrl step's loop (BaseAviary.py:343-372): rotation matrix, the optional force models, _dynamics.
+// `last` is a literal at both call sites (the final substep is peeled off the loop): only there ang_v = R_old·w_new
+// (BaseAviary.py:870) is observable, so in the looped substeps the rotation matrix dies before _integrateQ — 18 registers
+// less across the FP64 loop — and the three outputs are not carried through it.
+//   snap / le / nphys / t / active : MULTI only (downwash against the substep-start snapshot in shared memory)
+template <typename R, int KIND, bool MULTI>
+__device__ __forceinline__ void step_substep(const StepArgs<R>& a, State<R>& s, const Forcing<R>& F, const R (&rpm_r)[4],
+                                             R wsum, bool last, R& avx, R& avy, R& avz,
+                                             V4<R>* snap, int le, int nphys, int t, bool active)
+{
+    const DevDrone<R>& P = a.drone;
+    R m[9];
+    const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);    // :836 (shared with the force models)
+    if constexpr (KIND == GPD_K_LEAN) {
+        dyn_substep<R>(P, a.dt, s, m, omz, F, nullptr, nullptr, last, avx, avy, avz);
+    } else {
+        R gnd[4], fb[3] = { R(0), R(0), R(0) };
+        const R* pg = nullptr;
+        const R* pb = nullptr;
+        if (a.phy & GPD_PHY_GND) {
+            // The gate |roll|,|pitch| < pi/2 of the rpy snapshot (BaseAviary.py:346-347,518,742) needs only the signs of
+            // the atan2/asin arguments: |atan2(y,x)| < pi/2 <=> x > 0 (or x = y = 0); Bullet's gimbal branch
+            // (|s| >= 0.99999) returns pitch = +-pi/2 and fails the gate, otherwise |asin(s)| < pi/2.  Exact in both
+            // precisions up to atan2 results that ROUND to pi/2 (|y/x| > 1e16): three libm calls per substep saved.
+            const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
+            const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
+            const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
+            const R roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
+            const R pitch = gimbal ? R(GPD_PI) : R(0);
+            if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
+        }
+        if (a.phy & GPD_PHY_DRAG) {                          // :359,366: rpm = last_clipped_action
+            R db[3];
+            drag_body_w(P, wsum, m, s.vx, s.vy, s.vz, db);
+            fb[0] += db[0]; fb[1] += db[1]; fb[2] += db[2];
+            pb = fb;
+        }
+        if constexpr (MULTI) {
+            if (a.phy & GPD_PHY_DW) {                        // :362,367 against the substep-start snapshot
+                phys_sync(nphys);
+                if (t < a.DPB) snap[t] = M<R>::make4(s.px, s.py, s.pz, R(0));   // (x, y, z, -): one 16/32-byte read per pair
+                phys_sync(nphys);
+                R dw = R(0);
+                const V4<R>* env = snap + le * a.N;
+                if (active) {
+#pragma unroll 4
+                    for (int j = 0; j < a.N; ++j) {
+                        const V4<R> o = env[j];
+                        dw += downwash_pair(P, s.px, s.py, s.pz, o.x, o.y, o.z);
+                    }
+                }
+                fb[2] += dw;
+                pb = fb;
+            }
+        }
+        dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, last, avx, avy, avz);
+    }
+}
+
 // ============================================================================================
 // The fused step kernel: BaseAviary.step (BaseAviary.py:259-383).
 //   KIND  : which optional code the variant carries (each keeps its own register budget)
@@ -361,13 +438,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     const bool edge_smem = tma_copy && VEC && a.tma_edge;       // physics threads read the two edge slots from shared memory
     if (tma_copy && t == nphys) mbar_init(&tma_bar, 1);
     if (a.tile_dep) {
-        if (t == 0) {                   // claim this tile's sequence number and look at its completed count in one round trip
-            uint32_t* seq = a.tile_seq + (int64_t)bid * 8;
-            const uint32_t done0 = ld_acquire_gpu(seq + 1);
-            const uint32_t mine = atomicAdd(seq, 1u);          // steps claimed before this one
-            if (done0 != mine)
-                while (ld_acquire_gpu(seq + 1) != mine) __nanosleep(32);
-        }
+        if (t == 0) tile_claim_and_wait(a.tile_seq + (int64_t)bid * 4);
         __syncthreads();                // the claim is performed: dependents may start; the tile's previous step is visible
         if (a.pdl_trigger_early) pdl_launch_dependents();
     } else {
@@ -430,10 +501,15 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     float4 edge_lo = make_float4(0.f, 0.f, 0.f, 0.f), edge_hi = edge_lo;     // old ring slots 1 and B-1 (see the DMA warp)
     V4<R> tg = M<R>::make4(R(0), R(0), R(0), R(0)), ip0 = tg, iq0 = tg;
     const bool pre_init = a.auto_reset && !a.init_per_env;      // shared initial pose: fetch it now, off the epilogue's critical path
+    // FP64 (parity mode): these 24 doubles would sit in registers across the substep loop; they are fetched in the epilogue
+    // instead (per-index constants: L1/L2 hits), which is what keeps the FP64 variants inside their register budgets
+    constexpr bool EARLY_CONST = !M<R>::is_double;
     if (active) {
         load_state(a.p, d, s);
-        if (!ctrl) tg = a.p.target[a.target_per_env ? d : (int64_t)i];
-        if (pre_init) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
+        if constexpr (EARLY_CONST) {
+            if (!ctrl) tg = a.p.target[a.target_per_env ? d : (int64_t)i];
+            if (pre_init) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
+        }
         if (i == 0) {                   // per-env bookkeeping: loaded here so its DRAM latency hides behind the physics
             cnt = a.p.counter[e];
             if (a.auto_reset) ep_ret0 = a.p.ep_ret[e];
@@ -516,55 +592,11 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
         c.h = a.dt * .5f; c.hh = c.h * c.h;
         for (; sub0 < a.S - 1; ++sub0) lean_substep_f32(a.dt, s, c);
     }
-    for (int sub = sub0; sub < a.S; ++sub) {
-        R m[9];
-        const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);    // :836 (shared with the force models)
-        const bool last = sub == a.S - 1;
-        if constexpr (LEAN) {
-            dyn_substep<R>(P, a.dt, s, m, omz, F, nullptr, nullptr, last, avx, avy, avz);
-        } else {
-            R gnd[4], fb[3] = { R(0), R(0), R(0) };
-            const R* pg = nullptr;
-            const R* pb = nullptr;
-            if (a.phy & GPD_PHY_GND) {
-                // The gate |roll|,|pitch| < pi/2 of the rpy snapshot (BaseAviary.py:346-347,518,742) needs only the signs of
-                // the atan2/asin arguments: |atan2(y,x)| < pi/2 <=> x > 0 (or x = y = 0); Bullet's gimbal branch
-                // (|s| >= 0.99999) returns pitch = +-pi/2 and fails the gate, otherwise |asin(s)| < pi/2.  Exact in both
-                // precisions up to atan2 results that ROUND to pi/2 (|y/x| > 1e16): three libm calls per substep saved.
-                const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
-                const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
-                const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
-                const R roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
-                const R pitch = gimbal ? R(GPD_PI) : R(0);
-                if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
-            }
-            if (a.phy & GPD_PHY_DRAG) {                          // :359,366: rpm = last_clipped_action
-                R db[3];
-                drag_body_w(P, sub == 0 ? wsum_prev : wsum_cur, m, s.vx, s.vy, s.vz, db);
-                fb[0] += db[0]; fb[1] += db[1]; fb[2] += db[2];
-                pb = fb;
-            }
-            if constexpr (MULTI) {
-                if (a.phy & GPD_PHY_DW) {                        // :362,367 against the substep-start snapshot
-                    V4<R>* snap = reinterpret_cast<V4<R>*>(sm.snap());    // (x, y, z, -) per drone: one 16/32-byte read per pair
-                    phys_sync(nphys);
-                    if (t < a.DPB) snap[t] = M<R>::make4(s.px, s.py, s.pz, R(0));
-                    phys_sync(nphys);
-                    R dw = R(0);
-                    const V4<R>* env = snap + le * a.N;
-                    if (active) {
-#pragma unroll 4
-                        for (int j = 0; j < a.N; ++j) {
-                            const V4<R> o = env[j];
-                            dw += downwash_pair(P, s.px, s.py, s.pz, o.x, o.y, o.z);
-                        }
-                    }
-                    fb[2] += dw;
-                    pb = fb;
-                }
-            }
-            dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, last, avx, avy, avz);
-        }
+    {
+        V4<R>* snap = MULTI ? reinterpret_cast<V4<R>*>(sm.snap()) : nullptr;
+        for (int sub = sub0; sub < a.S - 1; ++sub)
+            step_substep<R, KIND, MULTI>(a, s, F, rpm_r, sub == 0 ? wsum_prev : wsum_cur, false, avx, avy, avz, snap, le, nphys, t, active);
+        step_substep<R, KIND, MULTI>(a, s, F, rpm_r, a.S == 1 ? wsum_prev : wsum_cur, true, avx, avy, avz, snap, le, nphys, t, active);
     }
 
     if (a.timeline && t == 0 && s.px == s.px) a.timeline[(int64_t)bid * 8 + 3] = gtime(); // 3: substeps done
@@ -574,6 +606,9 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
 
     R rew = R(-1);                      // CtrlAviary.py:144-200: dummy reward/flags
     int term = 0, trunc = 0;
+    if constexpr (!EARLY_CONST) {
+        if (active && !ctrl) tg = a.p.target[a.target_per_env ? d : (int64_t)i];
+    }
     if (!ctrl) {
         R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
         R dist = M<R>::sqrt(ex * ex + ey * ey + ez * ez);
@@ -663,6 +698,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
                 tk[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
             }
             if (pre_init) {             // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
+                if constexpr (!EARLY_CONST) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
                 s.px = ip0.x; s.py = ip0.y; s.pz = ip0.z;
                 s.qx = iq0.x; s.qy = iq0.y; s.qz = iq0.z; s.qw = iq0.w;
                 s.vx = s.vy = s.vz = R(0);
@@ -763,7 +799,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
     if (a.tile_dep) {
         if (ctrl) __syncthreads();      // the tile write-out above is part of what the next step of this tile reads
         // every global write of this CTA happened before the barrier(s) above: publish the tile (release, gpu scope)
-        if (t == 0) red_release_gpu_inc(a.tile_seq + (int64_t)bid * 8 + 1);
+        if (t == 0) tile_publish(a.tile_seq + (int64_t)bid * 4);
         // keep stream order transitive: this grid does not complete before the grids it was allowed to overtake
         pdl_wait();
     }

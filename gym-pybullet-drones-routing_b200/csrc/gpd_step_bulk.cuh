@@ -12,8 +12,9 @@
 //                            shifted ring already sits where the new row wants it (BaseRLAviary.py:187,317-318)
 //     the state tiles        sP, sQ, sV (16/32 B per env), sWz, step counter, episode return
 //     the action tile        T x 16 B
-// Every thread then integrates its drone from shared memory exactly as gpd::step_kernel does (same device functions, same
-// order of operations: results are bit-identical), patches its row (12 kin floats in front, this step's action in the newest
+// Every thread then integrates its drone exactly as gpd::step_kernel does (same device functions, same order of
+// operations: bit-identical in FP64; in FP32 the two kernels may differ in the compiler's FMA contraction, which is why a
+// handle never switches kernels between steps), patches its row (12 kin floats in front, this step's action in the newest
 // slot), writes its state / reward / flags back into shared memory; after one barrier thread 0 stores every tile back with
 // bulk copies (the observation tile as ONE contiguous 18 KB store).  Reading the full old rows costs 48 B per env more than
 // the shifted slots alone (the DRAM atom is 64 B: 32 of them were being fetched anyway); in exchange every byte moves in
@@ -36,30 +37,50 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// shared-memory carve-up of one tile (every region starts 16-byte aligned because T % 16 == 0)
+// shared-memory carve-up of one tile (every region starts 16-byte aligned because T % 16 == 0).  `direct` (StepArgs::
+// bulk_direct) says what does NOT go through shared memory — shared memory per env is what bounds the number of tiles
+// in flight per SM, and with it the launch's throughput (tiles in flight / lifetime of a tile):
+//     0  everything staged: 370 B per env (FP32, W = 72)                            9 tiles of 64 envs per SM
+//     1  the small per-env arrays (action, rates.z, reward, counter, episode return, flags: 34 B) are read and written
+//        by the drone's own thread: 336 B per env                                   10 tiles per SM
+//     2  the state vectors sP / sQ / sV too: 288 B per env (the observation tile)    11 tiles per SM
 template <typename R>
 struct BulkSmem {
     unsigned char* base;
-    int T, W;
+    int T, W, direct;
     __device__ float* obs() const { return reinterpret_cast<float*>(base); }
     __device__ V4<R>* sP() const { return reinterpret_cast<V4<R>*>(base + (size_t)T * W * 4); }
     __device__ V4<R>* sQ() const { return sP() + T; }
     __device__ V4<R>* sV() const { return sQ() + T; }
-    __device__ float4* act() const { return reinterpret_cast<float4*>(sV() + T); }
+    __device__ unsigned char* after_state() const { return reinterpret_cast<unsigned char*>(sP() + (direct >= 2 ? 0 : 3 * T)); }
+    // direct == 0 only:
+    __device__ float4* act() const { return reinterpret_cast<float4*>(after_state()); }
     __device__ R* sWz() const { return reinterpret_cast<R*>(act() + T); }
     __device__ R* rew() const { return sWz() + T; }
     __device__ int32_t* cnt() const { return reinterpret_cast<int32_t*>(rew() + T); }
     __device__ float* ep() const { return reinterpret_cast<float*>(cnt() + T); }
     __device__ uint8_t* term() const { return reinterpret_cast<uint8_t*>(ep() + T); }
     __device__ uint8_t* trunc() const { return term() + T; }
-    __device__ float* stat_f() const { return reinterpret_cast<float*>(trunc() + T); }
+    __device__ float* stat_f() const { return reinterpret_cast<float*>(direct ? after_state() : trunc() + T); }
     __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4 * 8); }      // up to 8 warps
+};
+
+// what a thread fetches itself before it waits for the tile (direct >= 1): issued right after the tile's dependency is
+// resolved, so the latency runs under the bulk loads
+template <typename R>
+struct BulkPre {
+    float4 act;
+    R wz;
+    int32_t cnt;
+    float ep;
+    V4<R> p4, q4, v4;       // direct == 2
 };
 
 // One thread's share of a tile: state / action / counters from shared memory, the arithmetic of gpd::step_kernel, results
 // back into the tile (plus the few per-drone extras that live only in global memory).  `sub` = timeline slot or -1.
 template <typename R, int KIND>
-__device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const BulkSmem<R>& sm, int t, int64_t row0, int rows, int tl)
+__device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const BulkSmem<R>& sm, const BulkPre<R>& pre, int t,
+                                                  int64_t row0, int rows, int tl)
 {
     constexpr bool LEAN = KIND == GPD_K_LEAN, HAS_PID = KIND == GPD_K_PID;
     const DevDrone<R>& P = a.drone;
@@ -70,9 +91,12 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
     V4<R> tg = M<R>::make4(R(0), R(0), R(0), R(0)), ip0 = tg, iq0 = tg;
     R rpm_prev[4] = { R(0), R(0), R(0), R(0) };
     const bool pre_init = a.auto_reset && !a.init_per_env;
+    constexpr bool EARLY_CONST = !M<R>::is_double;      // FP64: fetched in the epilogue (register budget, see gpd::step_kernel)
     if (active) {
-        tg = a.p.target[a.target_per_env ? d : (int64_t)0];
-        if (pre_init) { ip0 = a.p.init_pos[0]; iq0 = a.p.init_quat[0]; }
+        if constexpr (EARLY_CONST) {
+            tg = a.p.target[a.target_per_env ? d : (int64_t)0];
+            if (pre_init) { ip0 = a.p.init_pos[0]; iq0 = a.p.init_quat[0]; }
+        }
         if constexpr (!LEAN) {
             if (a.phy & GPD_PHY_DRAG) {
                 V4<R> v = a.p.aux_rpm[d];
@@ -86,16 +110,17 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
     float act[4] = { 0.f, 0.f, 0.f, 0.f };
     int32_t cnt = 0;
     float ep_ret0 = 0.f;
+    const int direct = sm.direct;
     if (active) {
-        const V4<R> p4 = sm.sP()[t], q4 = sm.sQ()[t], v4 = sm.sV()[t];
+        const V4<R> p4 = direct >= 2 ? pre.p4 : sm.sP()[t], q4 = direct >= 2 ? pre.q4 : sm.sQ()[t], v4 = direct >= 2 ? pre.v4 : sm.sV()[t];
         s.px = p4.x; s.py = p4.y; s.pz = p4.z; s.wx = p4.w;
         s.qx = q4.x; s.qy = q4.y; s.qz = q4.z; s.qw = q4.w;
         s.vx = v4.x; s.vy = v4.y; s.vz = v4.z; s.wy = v4.w;
-        s.wz = sm.sWz()[t];
-        const float4 av = sm.act()[t];
+        s.wz = direct ? pre.wz : sm.sWz()[t];
+        const float4 av = direct ? pre.act : sm.act()[t];
         act[0] = av.x; act[1] = av.y; act[2] = av.z; act[3] = av.w;
-        cnt = sm.cnt()[t];
-        if (a.auto_reset) ep_ret0 = sm.ep()[t];
+        cnt = direct ? pre.cnt : sm.cnt()[t];
+        if (a.auto_reset) ep_ret0 = direct ? pre.ep : sm.ep()[t];
     }
 
     // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238); A == 4: ActionType.RPM or ActionType.VEL ----
@@ -130,33 +155,9 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
         c.h = a.dt * .5f; c.hh = c.h * c.h;
         for (; sub0 < a.S - 1; ++sub0) lean_substep_f32(a.dt, s, c);
     }
-    for (int sub = sub0; sub < a.S; ++sub) {
-        R m[9];
-        const R omz = quat_to_mat(s.qx, s.qy, s.qz, s.qw, m);
-        const bool last = sub == a.S - 1;
-        if constexpr (LEAN) {
-            dyn_substep<R>(P, a.dt, s, m, omz, F, nullptr, nullptr, last, avx, avy, avz);
-        } else {
-            R gnd[4], fb[3] = { R(0), R(0), R(0) };
-            const R* pg = nullptr;
-            const R* pb = nullptr;
-            if (a.phy & GPD_PHY_GND) {      // same sign-based gate as gpd::step_kernel
-                const R sarg = R(-2) * (s.qx * s.qz - s.qw * s.qy);
-                const R rx = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz, ry = R(2) * (s.qy * s.qz + s.qw * s.qx);
-                const bool gimbal = sarg <= R(-0.99999) || sarg >= R(0.99999);
-                const R roll = gimbal ? R(0) : ((rx > R(0) || (rx == R(0) && ry == R(0))) ? R(0) : R(GPD_PI));
-                const R pitch = gimbal ? R(GPD_PI) : R(0);
-                if (ground_effect(P, rpm_r, s.pz, m, roll, pitch, gnd)) pg = gnd;
-            }
-            if (a.phy & GPD_PHY_DRAG) {
-                R db[3];
-                drag_body_w(P, sub == 0 ? wsum_prev : wsum_cur, m, s.vx, s.vy, s.vz, db);
-                fb[0] += db[0]; fb[1] += db[1]; fb[2] += db[2];
-                pb = fb;
-            }
-            dyn_substep<R>(P, a.dt, s, m, omz, F, pg, pb, last, avx, avy, avz);
-        }
-    }
+    for (int sub = sub0; sub < a.S - 1; ++sub)          // same device function as gpd::step_kernel (last substep peeled)
+        step_substep<R, KIND, false>(a, s, F, rpm_r, sub == 0 ? wsum_prev : wsum_cur, false, avx, avy, avz, nullptr, 0, 0, t, active);
+    step_substep<R, KIND, false>(a, s, F, rpm_r, a.S == 1 ? wsum_prev : wsum_cur, true, avx, avy, avz, nullptr, 0, 0, t, active);
     if (a.timeline && tl >= 0 && t == 0 && s.px == s.px) a.timeline[(int64_t)tl * 8 + 3] = gtime();
 
     // ---- _updateAndStoreKinematicInformation (BaseAviary.py:374,509-519) + outputs ----
@@ -164,6 +165,9 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
     quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
     R rew;
     int term, trunc;
+    if constexpr (!EARLY_CONST) {
+        if (active) tg = a.p.target[a.target_per_env ? d : (int64_t)0];
+    }
     {
         R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
         R dist = M<R>::sqrt(ex * ex + ey * ey + ez * ez);
@@ -221,6 +225,7 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
             tk[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
         }
         if (pre_init) {                     // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
+            if constexpr (!EARLY_CONST) { ip0 = a.p.init_pos[0]; iq0 = a.p.init_quat[0]; }
             s.px = ip0.x; s.py = ip0.y; s.pz = ip0.z;
             s.qx = iq0.x; s.qy = iq0.y; s.qz = iq0.z; s.qw = iq0.w;
             s.vx = s.vy = s.vz = R(0);
@@ -239,20 +244,34 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
 
     // ---- everything back into the tile ----
     if (active) {
-        sm.sP()[t] = M<R>::make4(s.px, s.py, s.pz, s.wx);
-        sm.sQ()[t] = M<R>::make4(s.qx, s.qy, s.qz, s.qw);
-        sm.sV()[t] = M<R>::make4(s.vx, s.vy, s.vz, s.wy);
-        sm.sWz()[t] = s.wz;
-        sm.cnt()[t] = done ? 0 : cnt + a.S;                             // BaseAviary.py:382
-        if (a.auto_reset) sm.ep()[t] = ep_new;
+        if (direct >= 2) {
+            a.p.sP[d] = M<R>::make4(s.px, s.py, s.pz, s.wx);
+            a.p.sQ[d] = M<R>::make4(s.qx, s.qy, s.qz, s.qw);
+            a.p.sV[d] = M<R>::make4(s.vx, s.vy, s.vz, s.wy);
+        } else {
+            sm.sP()[t] = M<R>::make4(s.px, s.py, s.pz, s.wx);
+            sm.sQ()[t] = M<R>::make4(s.qx, s.qy, s.qz, s.qw);
+            sm.sV()[t] = M<R>::make4(s.vx, s.vy, s.vz, s.wy);
+        }
+        const int32_t cnt_new = done ? 0 : cnt + a.S;                   // BaseAviary.py:382
+        if (direct) {
+            a.p.sWz[d] = s.wz;
+            a.p.counter[d] = cnt_new;
+            if (a.auto_reset) a.p.ep_ret[d] = ep_new;
+        } else {
+            sm.sWz()[t] = s.wz;
+            sm.cnt()[t] = cnt_new;
+            if (a.auto_reset) sm.ep()[t] = ep_new;
+        }
         float4* r = reinterpret_cast<float4*>(sm.obs() + (size_t)t * a.W);
         r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);             // BaseRLAviary.py:310-316
         r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
         r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
         r[(a.W >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);   // newest ring slot, BaseRLAviary.py:187
-        if (full) {
+        if (full && !direct && !a.out_plain) {
             sm.rew()[t] = rew; sm.term()[t] = (uint8_t)term; sm.trunc()[t] = (uint8_t)trunc;
-        } else {                            // ragged last tile: sizes are no multiples of 16 bytes, plain stores
+        } else {                            // direct mode, caller arrays that are not 16-byte aligned (e.g. rows of a [T][E] uint8 trajectory
+                                            // buffer), or the ragged last tile (sizes are no multiples of 16 bytes): plain stores
             if (a.reward) a.reward[d] = rew;
             if (a.terminated) a.terminated[d] = (uint8_t)term;
             if (a.truncated) a.truncated[d] = (uint8_t)trunc;
@@ -311,7 +330,8 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     const int t = threadIdx.x;
     const int bid = (int)blockIdx.x + a.cta0;
     const int T = a.DPB;
-    BulkSmem<R> sm{ smem_raw, T, a.W };
+    const int direct = a.bulk_direct;
+    BulkSmem<R> sm{ smem_raw, T, a.W, direct };
     const int64_t row0 = (int64_t)bid * T;
     const int rows = (int)min((int64_t)T, a.D - row0);
     const bool full = rows == T;
@@ -319,13 +339,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();
     if (t == 0) mbar_init(&bar, 1);
     if (a.tile_dep) {
-        if (t == 0) {
-            uint32_t* seq = a.tile_seq + (int64_t)bid * 8;
-            const uint32_t done0 = ld_acquire_gpu(seq + 1);
-            const uint32_t mine = atomicAdd(seq, 1u);
-            if (done0 != mine)
-                while (ld_acquire_gpu(seq + 1) != mine) __nanosleep(32);
-        }
+        if (t == 0 && !(a.dbg & 2)) tile_claim_and_wait(a.tile_seq + (int64_t)bid * 4);
         __syncthreads();
         if (a.pdl_trigger_early) pdl_launch_dependents();
     } else {
@@ -342,16 +356,31 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
         // the last tile of the buffer must not read past its end: its final row loses the 16 stray bytes
         const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((row0 + rows >= a.D) ? 16u : 0u) : 0u;
         const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
-        const uint32_t total = ob + 3 * st + (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u);
+        const uint32_t total = ob + (direct >= 2 ? 0u : 3 * st) + (direct ? 0u : (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u));
         mbar_expect_tx(&bar, total);
         if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + a.A, ob, &bar);
-        bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
-        bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
-        bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
-        bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
-        bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);                  // library arrays are padded to whole tiles
-        bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
-        if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
+        if (direct < 2) {
+            bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
+            bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
+            bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
+        }
+        if (!direct) {
+            bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
+            bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);              // library arrays are padded to whole tiles
+            bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
+            if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
+        }
+    }
+    BulkPre<R> pre;
+    pre.act = make_float4(0.f, 0.f, 0.f, 0.f); pre.wz = R(0); pre.cnt = 0; pre.ep = 0.f;
+    pre.p4 = pre.q4 = pre.v4 = M<R>::make4(R(0), R(0), R(0), R(0));
+    if (direct && t < rows) {               // the thread's own small inputs: in flight under the bulk loads
+        const int64_t d = row0 + t;
+        pre.act = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
+        pre.wz = a.p.sWz[d];
+        pre.cnt = a.p.counter[d];
+        if (a.auto_reset) pre.ep = a.p.ep_ret[d];
+        if (direct >= 2) { pre.p4 = a.p.sP[d]; pre.q4 = a.p.sQ[d]; pre.v4 = a.p.sV[d]; }
     }
     if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
         float* r = sm.obs() + (size_t)t * a.W;
@@ -360,7 +389,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     mbar_wait(&bar, 0);
     if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
 
-    bulk_tile_physics<R, KIND>(a, sm, t, row0, rows, bid);
+    bulk_tile_physics<R, KIND>(a, sm, pre, t, row0, rows, bid);
     fence_proxy_async_smem();               // this thread's shared-memory writes -> the bulk stores below
     __syncthreads();
     if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();
@@ -369,13 +398,17 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
         const uint32_t v4b = (uint32_t)sizeof(V4<R>);
         const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
         bulk_s2g(reinterpret_cast<float*>(a.obs_out) + row0 * a.W, sm.obs(), (uint32_t)rows * a.W * 4);
-        bulk_s2g(a.p.sP + row0, sm.sP(), st);
-        bulk_s2g(a.p.sQ + row0, sm.sQ(), st);
-        bulk_s2g(a.p.sV + row0, sm.sV(), st);
-        bulk_s2g(a.p.sWz + row0, sm.sWz(), sc);
-        bulk_s2g(a.p.counter + row0, sm.cnt(), i4);
-        if (a.auto_reset) bulk_s2g(a.p.ep_ret + row0, sm.ep(), i4);
-        if (full) {
+        if (direct < 2) {
+            bulk_s2g(a.p.sP + row0, sm.sP(), st);
+            bulk_s2g(a.p.sQ + row0, sm.sQ(), st);
+            bulk_s2g(a.p.sV + row0, sm.sV(), st);
+        }
+        if (!direct) {
+            bulk_s2g(a.p.sWz + row0, sm.sWz(), sc);
+            bulk_s2g(a.p.counter + row0, sm.cnt(), i4);
+            if (a.auto_reset) bulk_s2g(a.p.ep_ret + row0, sm.ep(), i4);
+        }
+        if (full && !direct && !a.out_plain) {
             if (a.reward) bulk_s2g(a.reward + row0, sm.rew(), sc);
             if (a.terminated) bulk_s2g(a.terminated + row0, sm.term(), (uint32_t)T);
             if (a.truncated) bulk_s2g(a.truncated + row0, sm.trunc(), (uint32_t)T);
@@ -383,8 +416,9 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         bulk_tile_stats<R>(a, sm, bid, rows);
         if (a.tile_dep) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
-            red_release_gpu_inc(a.tile_seq + (int64_t)bid * 8 + 1);
+            if (a.dbg & 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
+            if (!(a.dbg & 2)) tile_publish(a.tile_seq + (int64_t)bid * 4);
         } else {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }

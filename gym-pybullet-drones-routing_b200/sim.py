@@ -122,6 +122,13 @@ class BatchedSim:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_step_chaining(self, enable: bool = True):
+        """Chained stepping (gpd_set_step_chaining, default off): back-to-back step() calls of one stream overlap across the
+        kernel boundary, each tile waiting only for its own previous step.  Only valid when the actions of every step
+        were complete before the PREVIOUS kernel of the stream was enqueued (a pre-computed action schedule, action repeat,
+        independent env sets stepped in rotation) — never behind the policy kernel that computes them."""
+        _lib.check(self.lib.gpd_set_step_chaining(self.h, int(bool(enable))))
+
     def set_targets(self, target_pos):
         """TARGET_POS (HoverAviary.py:51, MultiHoverAviary.py:71): (N,3) shared by every env or (E,N,3) per env."""
         t = np.ascontiguousarray(np.asarray(target_pos, dtype=np.float64))

@@ -154,6 +154,22 @@ int gpd_reset(gpd_sim* sim, const uint8_t* env_mask, const void* obs_prev, void*
 int gpd_step(gpd_sim* sim, const void* actions, const void* obs_prev, void* obs_out,
              void* reward, uint8_t* terminated, uint8_t* truncated, void* terminal_kin, void* stream);
 
+/*
+ * Chained stepping (default OFF).  BaseAviary.step calls are strictly ordered (BaseAviary.py:259-383 returns before the
+ * next call starts); gpd_step keeps that order on its stream: a step kernel starts only after ALL earlier work of the
+ * stream has completed and its results are visible.  A caller whose step inputs do not depend on the work enqueued just
+ * before the step — a pre-computed action schedule, an action repeated over k steps (frame skip), several independent
+ * env sets stepped in rotation on one stream — may turn chaining on: consecutive gpd_step launches of the stream are then
+ * launched programmatically (the next kernel starts while the previous one drains) and each tile of a handle waits only
+ * for ITS OWN previous step (one 64-bit word per tile), so results are bit-identical to unchained stepping.
+ * CONTRACT while chaining is on: `actions` (and every other input that is not this handle's own state or its previous
+ * observation) must have been complete BEFORE the previous kernel of the stream was enqueued; never chain a step behind
+ * the kernel that computes its actions (a policy network).  The library itself never chains the first step after
+ * gpd_reset / gpd_set_state / gpd_set_* on a handle, nor a step issued on a different stream than the handle's last one.
+ * No effect on shapes the library runs without per-tile sequencing (launches of more than ~4 waves).
+ */
+int gpd_set_step_chaining(gpd_sim* sim, int enable);
+
 /* Host-buffer variant of gpd_step for numpy-style call sites (the reference's own step() signature): copies
  * `actions` from host memory, runs gpd_step on internal device buffers (an internal obs ping-pong pair), copies
  * obs/reward/terminated/truncated back and synchronises `stream`. Host pointers may be pageable or pinned.

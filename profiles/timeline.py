@@ -25,6 +25,7 @@ g = torch.Generator(device="cuda"); g.manual_seed(0)
 acts = [(torch.rand((E, 1, 4), generator=g, device="cuda") * 2 - 1) for _ in range(2 * nsets)]
 for e in envs:
     e.reset()
+    e._sim.set_step_chaining(True)      # pre-generated actions: launches overlap across the kernel boundary
 for rep in range(4):
     for k in range(2 * nsets):
         envs[k % nsets]._sim.step(acts[k])
@@ -42,6 +43,8 @@ for _ in range(5):
     gr.replay()
 torch.cuda.synchronize()
 names = ["cta_start", "pdl_wait_done", "state_arrived", "substeps_done", "phys_stored", "tma_loaded", "tma_store_read", "barrier"]
+if os.environ.get("GPD_BULK", "1") != "0":     # phases of gpd::step_kernel_bulk (single-drone RL shapes)
+    names = ["cta_start", "tile_claimed", "tile_loaded", "substeps_done", "tile_patched", "-", "-", "tile_published"]
 # the last replay wrote each buffer twice (period 2*nsets); look at set 3's last launch and its predecessor (set 2)
 t3 = bufs[3 % nsets].cpu().numpy().astype(np.int64)
 t2 = bufs[2 % nsets].cpu().numpy().astype(np.int64)

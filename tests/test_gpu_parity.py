@@ -916,7 +916,7 @@ def test_cuda_bench_contract_line(extra):
     assert d["e2e"]["host_obs_equals_device_obs"] is True
     assert len(d["trials_ms"]) == 5 and d["rank_ms"]["max"] >= d["rank_ms"]["min"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
-    assert d["config"]["streams"] == (2 if "--streams" in extra else 1)
+    assert d["measurement"]["streams"] == (2 if "--streams" in extra else 1) and "l2" in d["config"]
     if not extra or "--steps" in extra:                             # informational multi-stream figure beside the headline
         assert d["async_pools"]["streams"] == 2 and d["async_pools"]["ms_per_step"] > 0
     else:

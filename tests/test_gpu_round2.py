@@ -200,6 +200,7 @@ def test_cuda_per_cta_sequencing_is_bit_identical_to_serial_launches(shape, monk
            "hoverpid_f32": (_kw(act="pid", freq=48, model=DroneModel.CF2P), 30000, "f32", True)}[shape]
     kw, E, prec, ar = cfg
     fast = make_sim(kw, E, prec, auto_reset=ar)
+    fast.set_step_chaining(True)        # the action buffers below are complete long before the first step is enqueued
     monkeypatch.setenv("GPD_TILE_DEP", "0"); monkeypatch.setenv("GPD_PDL", "0")
     slow = make_sim(kw, E, prec, auto_reset=ar)
     monkeypatch.delenv("GPD_TILE_DEP"); monkeypatch.delenv("GPD_PDL")
@@ -353,10 +354,13 @@ print("rank", rank, "ok")
         env.close()
 
 
-@pytest.mark.parametrize("act,flags,precision,freq,E", [("rpm", 0, "f64", 30, 1000), ("rpm", 0, "f64", 48, 333), ("rpm", 3, "f64", 30, 200),
-                                                         ("vel", 0, "f64", 48, 777), ("vel", 2, "f64", 48, 130), ("rpm", 0, "f64", 240, 4096),
-                                                         ("rpm", 0, "f32", 30, 1000), ("rpm", 3, "f32", 30, 517), ("vel", 0, "f32", 48, 300)])
-def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, freq, E, monkeypatch):
+@pytest.mark.parametrize("act,flags,precision,freq,E,direct", [
+    ("rpm", 0, "f64", 30, 1000, 2), ("rpm", 0, "f64", 48, 333, 2), ("rpm", 3, "f64", 30, 200, 2), ("vel", 0, "f64", 48, 777, 2),
+    ("vel", 2, "f64", 48, 130, 2), ("rpm", 0, "f64", 240, 4096, 2), ("rpm", 0, "f32", 30, 1000, 2), ("rpm", 3, "f32", 30, 517, 2),
+    ("vel", 0, "f32", 48, 300, 2),
+    # what bypasses shared memory in the bulk kernel (GPD_BULK_DIRECT): 0 = nothing, 1 = the small per-env arrays
+    ("rpm", 0, "f64", 30, 1000, 0), ("rpm", 3, "f64", 30, 200, 1), ("vel", 2, "f64", 48, 130, 0), ("rpm", 0, "f32", 30, 1000, 1)])
+def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, freq, E, direct, monkeypatch):
     """Single-drone RL envs with 4-wide actions run the bulk-copy data path (gpd_step_bulk.cuh) by default.  Against the
     per-thread / TMA-box kernel (GPD_BULK=0), FP64: identical bits in state, observation, reward, flags, terminal rows and
     episode statistics, with ragged last tiles, per-env initial poses, auto-reset, force models and the in-loop controller,
@@ -368,8 +372,10 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
     xyz = rng.uniform([-1, -1, 0.2], [1, 1, 1.5], size=(E, 1, 3))
     rpy = rng.uniform(-0.2, 0.2, size=(E, 1, 3))
     kw["init_xyz"], kw["init_rpy"] = xyz, rpy
-    monkeypatch.setenv("GPD_BULK", "1")           # force the bulk path also where the default would not pick it (48 Hz rows)
+    monkeypatch.setenv("GPD_BULK", "1")           # force the bulk path also where the default would not pick it (240 Hz rows)
+    monkeypatch.setenv("GPD_BULK_DIRECT", str(direct))
     bulk = make_sim(kw, E, precision, auto_reset=f64)
+    monkeypatch.delenv("GPD_BULK_DIRECT")
     monkeypatch.setenv("GPD_BULK", "0")
     ref = make_sim(kw, E, precision, auto_reset=f64)
     monkeypatch.delenv("GPD_BULK")
@@ -413,3 +419,4 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
         sb, sr = bulk.episode_stats(), ref.episode_stats()
         assert np.array_equal(sb, sr) and (sb[0] > 0 or freq == 240)
     bulk.close(); ref.close()
+
