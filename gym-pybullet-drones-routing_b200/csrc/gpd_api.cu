@@ -205,6 +205,7 @@ static void fill_drone(const gpd_drone_params& p, DevDrone<R>& d)
 {
     d.model = p.model;
     d.M = (R)p.M; d.L = (R)p.L; d.ARM = (R)(p.L / std::sqrt(2.0));
+    d.INV_M = (R)(1.0 / p.M);
     d.KF = (R)p.KF; d.KM = (R)p.KM;
     for (int k = 0; k < 3; ++k) { d.J[k] = (R)p.J[k]; d.JINV[k] = (R)p.J_INV[k]; d.DRAG[k] = (R)p.DRAG_COEFF[k]; }
     d.GRAVITY = (R)p.GRAVITY; d.MAX_RPM = (R)p.MAX_RPM;
@@ -389,7 +390,6 @@ static int build_args(gpd_sim* s, StepArgs<R>& a)
     }
     a.tma_edge_bytes = s->tma_edge_bytes;
     a.bulk_direct = s->bulk_direct;
-    a.dbg = getenv("GPD_DEBUG_UNSAFE") ? atoi(getenv("GPD_DEBUG_UNSAFE")) : 0;
     a.use_tma = 0;
     a.EPB = a.DPB / c.num_drones;
     // default initial poses, BaseAviary.py:194-207
@@ -572,9 +572,9 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         // vectors bypass shared memory (direct = 2; with everything staged the TMA-box kernel was ahead there).  Longer rows
         // (60 Hz and up) leave too few tiles per SM.  GPD_BULK=1 forces it where eligible, GPD_BULK=0 turns it off.
         const char* ev = getenv("GPD_BULK");
-        const bool eligible = !ctrl && N == 1 && A == 4 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 &&
-                              bsm <= (size_t)smem_optin &&
-                              (cfg->action_type == GPD_ACT_RPM || cfg->action_type == GPD_ACT_VEL);
+        // narrower actions (PID: A = 3, ONE_D_*: A = 1) slide their rows inside shared memory and take their actions per thread
+        const bool eligible = !ctrl && N == 1 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 && bsm <= (size_t)smem_optin &&
+                              (A == 4 || direct == 2);
         s->bulk_ok = eligible && (ev ? atoi(ev) != 0 : s->W * 4 <= 512);
         s->lc_bulk.threads = DPB; s->lc_bulk.grid = L.grid; s->lc_bulk.smem = bsm; s->lc_bulk.pdl = 0;
     }

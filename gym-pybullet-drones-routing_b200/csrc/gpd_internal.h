@@ -35,6 +35,7 @@ struct DevDrone {
     R DT_EULER[3];          // FP32 mode: PYB_TIMESTEP*J^-1[k]*(J[k+2]-J[k+1]), the gyroscopic coefficients of the diagonal J
     R J[3], JINV[3];
     R M, L, ARM;            // ARM = L/sqrt(2)  (BaseAviary.py:847-848)
+    R INV_M;                // RN(1/M), for div_by_const (FP64 kernels)
     R KF, KM;
     // ---- cold: force models ----
     R GND_EFF_COEFF, PROP_RADIUS, GND_EFF_H_CLIP;
@@ -108,7 +109,6 @@ struct StepArgs {
     int32_t target_per_env; // 1: p.target holds D entries (per-env MultiHover targets), else N
     int32_t cta0;           // first CTA of this launch (0 unless the step is issued in chunks)
     int32_t out_plain;      // bulk path, per call: reward / terminated / truncated are not all 16-byte aligned -> plain stores by the threads
-    int32_t dbg;            // EXPERIMENTS ONLY (GPD_DEBUG_UNSAFE): bit 0 = publish a tile without waiting for its stores, bit 1 = skip the claim
     int32_t bulk_direct;    // bulk path: what bypasses shared memory (0 nothing, 1 the small per-env arrays, 2 the state vectors too)
     SimPtrs<R> p;
     DevDrone<R> drone;

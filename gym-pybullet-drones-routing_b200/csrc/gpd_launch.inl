@@ -136,7 +136,7 @@ static cudaError_t ensure_bulk_smem(size_t need)
 
 static int bulk_kind(int action_type, int phy)
 {
-    const bool rpm_like = action_type == GPD_ACT_RPM;
+    const bool rpm_like = action_type == GPD_ACT_RPM || action_type == GPD_ACT_ONE_D_RPM;
     return !rpm_like ? GPD_K_PID : (phy == 0 ? GPD_K_LEAN : GPD_K_FORCES);
 }
 

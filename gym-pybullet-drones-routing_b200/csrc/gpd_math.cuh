@@ -56,6 +56,22 @@ template <> struct M<double> {
     static __device__ __forceinline__ double4 make4(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
 };
 
+// a / b for a divisor that is constant over the launch, with rb = RN(1/b) computed on the host: q0 = RN(a*rb),
+// r = a - q0*b (exact in one FMA), q = RN(q0 + r*rb).  By Markstein's theorem q is the CORRECTLY ROUNDED quotient — the
+// same bits as a / b — whenever rb is the correctly rounded reciprocal and nothing over- or underflows; outside a wide
+// safe range of |a| (which also covers +-0, inf, NaN) the plain division runs.  3 FMA-pipe instructions instead of the
+// ~12-instruction IEEE division sequence, three times per substep in the FP64 kernels (F / M, BaseAviary.py:855).
+// tests/test_div_const_cpu.py checks the identity bit for bit on 3e7 random operands for every drone mass.
+__device__ __forceinline__ double div_by_const(double a, double b, double rb)
+{
+    const double m = fabs(a);
+    if (!(m > 1e-280 && m < 1e280)) return a / b;
+    const double q0 = a * rb;
+    const double r = fma(-q0, b, a);
+    return fma(r, rb, q0);
+}
+__device__ __forceinline__ float div_by_const(float a, float b, float) { return a / b; }
+
 #define GPD_PI 3.14159265358979323846
 
 template <typename R>
@@ -330,7 +346,7 @@ __device__ __forceinline__ void dyn_substep(const DevDrone<R>& P, R dt, State<R>
     R gx = s.wy * Jz - s.wz * Jy, gy = s.wz * Jx - s.wx * Jz, gz = s.wx * Jy - s.wy * Jx;
     if constexpr (M<R>::is_double) {
         R dwx = P.JINV[0] * (tx - gx), dwy = P.JINV[1] * (ty - gy), dwz = P.JINV[2] * (tz - gz);   // :854
-        R ax = Fx / P.M, ay = Fy / P.M, az = Fz / P.M;                                     // :855
+        R ax = div_by_const(Fx, P.M, P.INV_M), ay = div_by_const(Fy, P.M, P.INV_M), az = div_by_const(Fz, P.M, P.INV_M);   // :855, same bits as F / M
         s.vx = s.vx + dt * ax; s.vy = s.vy + dt * ay; s.vz = s.vz + dt * az;               // :857
         s.wx = s.wx + dt * dwx; s.wy = s.wy + dt * dwy; s.wz = s.wz + dt * dwz;            // :858
     } else {                                                     // same updates with dt/M and dt*J^-1 folded on the host

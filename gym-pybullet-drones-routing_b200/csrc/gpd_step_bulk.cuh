@@ -1,5 +1,5 @@
-// gpd_step_bulk.cuh — the fused step kernel of the single-drone RL envs with 4-wide actions (HoverAviary with
-// ActionType.RPM / VEL: the BASELINE headline shape), with ALL of its HBM traffic moved by bulk asynchronous copies.
+// gpd_step_bulk.cuh — the fused step kernel of the single-drone RL envs (HoverAviary with any ActionType: the BASELINE
+// headline shape and the DSLPID-in-the-loop shape C5), with the observation tile moved by bulk asynchronous copies.
 //
 // Why a second data path (measured, profiles/stream_microbench.cu, 65,536 envs, 8 rotating sets, PDL): a plain streaming
 // kernel moves this launch's bytes in 7.0 us; the step's own 14 address streams accessed per thread take 12.2 us; the same
@@ -12,6 +12,11 @@
 //                            shifted ring already sits where the new row wants it (BaseRLAviary.py:187,317-318)
 //     the state tiles        sP, sQ, sV (16/32 B per env), sWz, step counter, episode return
 //     the action tile        T x 16 B
+// Actions narrower than a float4 (ActionType.PID: A = 3, ONE_D_*: A = 1; rows still 16-byte granular): a bulk copy cannot
+// shift by 12 bytes, so the tile is loaded UNSHIFTED and every thread slides its own row by A floats inside shared memory
+// (aligned float4 reads, a register funnel, aligned float4 writes, in place and conflict-free: consecutive rows start 21 or
+// 6 sixteen-byte units apart) — instead of one 32-lane warp funnelling the whole tile to global memory, which was the
+// limiter of gpd::step_kernel on these shapes (C5: 11 % of the stall samples on its stores, 11 % on the barrier behind it).
 // Every thread then integrates its drone exactly as gpd::step_kernel does (same device functions, same order of
 // operations: bit-identical in FP64; in FP32 the two kernels may differ in the compiler's FMA contraction, which is why a
 // handle never switches kernels between steps), patches its row (12 kin floats in front, this step's action in the newest
@@ -36,6 +41,28 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// out = the float4 that starts A floats into (lo, hi)
+template <int A>
+__device__ __forceinline__ float4 funnel4(const float4& lo, const float4& hi)
+{
+    if (A == 1) return make_float4(lo.y, lo.z, lo.w, hi.x);
+    if (A == 2) return make_float4(lo.z, lo.w, hi.x, hi.y);
+    return make_float4(lo.w, hi.x, hi.y, hi.z);
+}
+// one row of the tile, in place: ring slots move up by A floats, the newest slot receives this step's action
+template <int A>
+__device__ __forceinline__ void slide_row(float4* r, int W4, const float* act)
+{
+    float4 lo = r[3];
+#pragma unroll 4
+    for (int k = 3; k < W4 - 1; ++k) {
+        const float4 hi = r[k + 1];
+        r[k] = funnel4<A>(lo, hi);
+        lo = hi;
+    }
+    r[W4 - 1] = funnel4<A>(lo, make_float4(act[0], act[1], act[2], 0.f));
+}
 
 // shared-memory carve-up of one tile (every region starts 16-byte aligned because T % 16 == 0).  `direct` (StepArgs::
 // bulk_direct) says what does NOT go through shared memory — shared memory per env is what bounds the number of tiles
@@ -123,14 +150,17 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
         if (a.auto_reset) ep_ret0 = direct ? pre.ep : sm.ep()[t];
     }
 
-    // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238); A == 4: ActionType.RPM or ActionType.VEL ----
+    // ---- _preprocessAction -> rpm (BaseRLAviary.py:189-238) ----
     double rpm[4] = { 0., 0., 0., 0. };
     if (a.action_type == GPD_ACT_RPM) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) rpm[k] = P.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[k]));   // :192, float32 inner ops
+    } else if (a.action_type == GPD_ACT_ONE_D_RPM) {
+        const double v = P.HOVER_RPM_d * (double)__fadd_rn(1.0f, __fmul_rn(0.05f, act[0]));                       // :225
+        rpm[0] = rpm[1] = rpm[2] = rpm[3] = v;
     }
     if constexpr (HAS_PID) {
-        if (a.action_type == GPD_ACT_VEL && active) {
+        if ((a.action_type == GPD_ACT_VEL || a.action_type == GPD_ACT_PID || a.action_type == GPD_ACT_ONE_D_PID) && active) {
             R r4[4];
             pid_action(a, d, s, act, r4);
             rpm[0] = r4[0]; rpm[1] = r4[1]; rpm[2] = r4[2]; rpm[3] = r4[3];
@@ -264,10 +294,13 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
             if (a.auto_reset) sm.ep()[t] = ep_new;
         }
         float4* r = reinterpret_cast<float4*>(sm.obs() + (size_t)t * a.W);
+        if (a.A == 4) r[(a.W >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);   // newest ring slot, BaseRLAviary.py:187
+        else if (a.A == 3) slide_row<3>(r, a.W >> 2, act);              // the tile was loaded unshifted: slide the ring here
+        else if (a.A == 2) slide_row<2>(r, a.W >> 2, act);
+        else slide_row<1>(r, a.W >> 2, act);
         r[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);             // BaseRLAviary.py:310-316
         r[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
         r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
-        r[(a.W >> 2) - 1] = make_float4(act[0], act[1], act[2], act[3]);   // newest ring slot, BaseRLAviary.py:187
         if (full && !direct && !a.out_plain) {
             sm.rew()[t] = rew; sm.term()[t] = (uint8_t)term; sm.trunc()[t] = (uint8_t)trunc;
         } else {                            // direct mode, caller arrays that are not 16-byte aligned (e.g. rows of a [T][E] uint8 trajectory
@@ -339,7 +372,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();
     if (t == 0) mbar_init(&bar, 1);
     if (a.tile_dep) {
-        if (t == 0 && !(a.dbg & 2)) tile_claim_and_wait(a.tile_seq + (int64_t)bid * 4);
+        if (t == 0) tile_claim_and_wait(a.tile_seq + (int64_t)bid * 4);
         __syncthreads();
         if (a.pdl_trigger_early) pdl_launch_dependents();
     } else {
@@ -353,12 +386,14 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     if (t == 0) {
         fence_proxy_async_global();         // generic-proxy writes of the tile's previous step (ragged tails) -> bulk reads
         const uint32_t v4b = (uint32_t)sizeof(V4<R>);
-        // the last tile of the buffer must not read past its end: its final row loses the 16 stray bytes
-        const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((row0 + rows >= a.D) ? 16u : 0u) : 0u;
+        // A == 4: read at +A floats (already shifted); the last tile of the buffer must not read past its end: its final row
+        // loses the 16 stray bytes.  A < 4: whole rows, unshifted (slide_row)
+        const uint32_t shift = a.A == 4 ? 4u : 0u;
+        const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((shift && row0 + rows >= a.D) ? 16u : 0u) : 0u;
         const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
         const uint32_t total = ob + (direct >= 2 ? 0u : 3 * st) + (direct ? 0u : (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u));
         mbar_expect_tx(&bar, total);
-        if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + a.A, ob, &bar);
+        if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + shift, ob, &bar);
         if (direct < 2) {
             bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
             bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
@@ -376,7 +411,14 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
     pre.p4 = pre.q4 = pre.v4 = M<R>::make4(R(0), R(0), R(0), R(0));
     if (direct && t < rows) {               // the thread's own small inputs: in flight under the bulk loads
         const int64_t d = row0 + t;
-        pre.act = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
+        if (a.A == 4) {
+            pre.act = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
+        } else {
+            const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
+            pre.act.x = __ldg(ap);
+            if (a.A > 1) pre.act.y = __ldg(ap + 1);
+            if (a.A > 2) pre.act.z = __ldg(ap + 2);
+        }
         pre.wz = a.p.sWz[d];
         pre.cnt = a.p.counter[d];
         if (a.auto_reset) pre.ep = a.p.ep_ret[d];
@@ -416,9 +458,11 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         bulk_tile_stats<R>(a, sm, bid, rows);
         if (a.tile_dep) {
-            if (a.dbg & 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
-            if (!(a.dbg & 2)) tile_publish(a.tile_seq + (int64_t)bid * 4);
+            // Measured (profiles/r02/sweep_b6..b8.jsonl, unsafe experiments): waiting for the stores costs nothing; the claim
+            // (ATOMG + L1 invalidate) ~0.5 us and the release fence below (MEMBAR.ALL.GPU) ~0.6 us of an 8.6 us step.  A relaxed
+            // publish would be faster and is not a release pattern: the next step of this tile could then read stale state.
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
+            tile_publish(a.tile_seq + (int64_t)bid * 4);
         } else {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }

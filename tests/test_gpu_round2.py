@@ -359,9 +359,12 @@ print("rank", rank, "ok")
     ("vel", 2, "f64", 48, 130, 2), ("rpm", 0, "f64", 240, 4096, 2), ("rpm", 0, "f32", 30, 1000, 2), ("rpm", 3, "f32", 30, 517, 2),
     ("vel", 0, "f32", 48, 300, 2),
     # what bypasses shared memory in the bulk kernel (GPD_BULK_DIRECT): 0 = nothing, 1 = the small per-env arrays
-    ("rpm", 0, "f64", 30, 1000, 0), ("rpm", 3, "f64", 30, 200, 1), ("vel", 2, "f64", 48, 130, 0), ("rpm", 0, "f32", 30, 1000, 1)])
+    ("rpm", 0, "f64", 30, 1000, 0), ("rpm", 3, "f64", 30, 200, 1), ("vel", 2, "f64", 48, 130, 0), ("rpm", 0, "f32", 30, 1000, 1),
+    # actions narrower than a float4: the tile is loaded unshifted and every thread slides its own row in shared memory
+    ("pid", 0, "f64", 48, 500, 2), ("pid", 3, "f64", 48, 131, 2), ("one_d_rpm", 0, "f64", 48, 257, 2), ("one_d_pid", 0, "f64", 48, 200, 2),
+    ("one_d_rpm", 0, "f64", 240, 100, 2), ("pid", 0, "f32", 48, 300, 2)])
 def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, freq, E, direct, monkeypatch):
-    """Single-drone RL envs with 4-wide actions run the bulk-copy data path (gpd_step_bulk.cuh) by default.  Against the
+    """Single-drone RL envs run the bulk-copy data path (gpd_step_bulk.cuh) by default.  Against the
     per-thread / TMA-box kernel (GPD_BULK=0), FP64: identical bits in state, observation, reward, flags, terminal rows and
     episode statistics, with ragged last tiles, per-env initial poses, auto-reset, force models and the in-loop controller,
     a first step without a previous observation and a masked reset.  FP32 (FMA contraction is free to differ between two
@@ -394,14 +397,15 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
         for u, v in zip(bulk.get_state(), ref.get_state()):
             close(u, v, tag)
     # a first step with NO previous observation (all-zero ring), then the regular chain
-    a0 = torch.from_numpy(rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)).cuda()
+    A = bulk.A
+    a0 = torch.from_numpy(rng.uniform(-1, 1, (E, 1, A)).astype(np.float32)).cuda()
     for sim in (bulk, ref):
         sim._have_prev = False
     for u, v in zip(bulk.step(a0)[:2], ref.step(a0)[:2]):
         close(u, v, "first step")
     same("first step")
     for t in range(40 if f64 else 8):
-        a = torch.from_numpy(rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)).cuda()
+        a = torch.from_numpy(rng.uniform(-1, 1, (E, 1, A)).astype(np.float32)).cuda()
         ob, oref = bulk.step(a), ref.step(a)
         for u, v in zip(ob[:2], oref[:2]):
             close(u, v, t)
