@@ -6,7 +6,7 @@ OUT="$HERE/../lib"
 mkdir -p "$OUT" "$HERE/obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $ARCH"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $ARCH ${GPD_NVCC_EXTRA:-}"
 "$NVCC" $COMMON -c "$HERE/gpd_f32.cu" -o "$HERE/obj/gpd_f32.o" 2> "$HERE/obj/ptxas_f32.log" &
 "$NVCC" $COMMON -fmad=false -c "$HERE/gpd_f64.cu" -o "$HERE/obj/gpd_f64.o" 2> "$HERE/obj/ptxas_f64.log" &
 "$NVCC" $COMMON -c "$HERE/gpd_api.cu" -o "$HERE/obj/gpd_api.o" 2> "$HERE/obj/ptxas_api.log" &

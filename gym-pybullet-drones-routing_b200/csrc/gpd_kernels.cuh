@@ -405,9 +405,14 @@ __device__ __forceinline__ void step_substep(const StepArgs<R>& a, State<R>& s, 
 // ============================================================================================
 template <typename R, int KIND, bool MULTI, bool VEC>
 // FP64: occupancy beats spill-free code.  Multi-drone: 128 registers (two 256-thread CTAs per SM) instead of 168 is 1.2-1.4x
-// faster (C3, C4); single-drone: 96 registers (four 160-thread CTAs) instead of 141-168 is 1.1-1.26x faster (65,536 .. 1 M envs);
-// 80 registers lose again (measured, profiles/README.md).
-__global__ void __launch_bounds__(MULTI ? (sizeof(R) == 8 ? 256 : 288) : 160, MULTI ? (sizeof(R) == 8 ? 2 : 1) : (sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 6 : (KIND == GPD_K_PID ? 5 : 4)) : 4))
+// faster (C3, C4) and no longer spills since the last substep is peeled and the epilogue constants are fetched late;
+// single-drone (the shapes the bulk kernel does not take): 96 registers (four 160-thread CTAs) with 70-380 bytes of spills
+// stay 0-32 % faster than the spill-free 128-register build (GPD_F64_SINGLE_MINB=3; profiles/r02/f64_single_register_cap.jsonl:
+// CtrlAviary x1 8.07 vs 9.13 us, ONE_D_RPM at 30 Hz 17.3 vs 22.9 us, PID at 30 Hz 41.4 vs 48.5 us); 80 registers lose again.
+#ifndef GPD_F64_SINGLE_MINB
+#define GPD_F64_SINGLE_MINB 4
+#endif
+__global__ void __launch_bounds__(MULTI ? (sizeof(R) == 8 ? 256 : 288) : 160, MULTI ? (sizeof(R) == 8 ? 2 : 1) : (sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 6 : (KIND == GPD_K_PID ? 5 : 4)) : GPD_F64_SINGLE_MINB))
 step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUtensorMap tm_prev,
             const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_edge)
 {

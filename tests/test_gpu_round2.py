@@ -424,3 +424,20 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
         assert np.array_equal(sb, sr) and (sb[0] > 0 or freq == 240)
     bulk.close(); ref.close()
 
+
+
+def test_oracle_matches_the_staged_reference_on_this_box():
+    """The CPU arm of bench.py runs the unmodified reference Python staged under oracle/_ref.  On the GPU box (where
+    /root/reference does not exist) replay random configurations in that copy and in the oracle: the checker of every parity
+    test here is pinned to the live reference on this very machine, not only to the committed fixtures."""
+    import json
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "gym_pybullet_drones")):
+        pytest.skip("oracle/_ref not staged (python oracle/stage_reference.py in the build container)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_vs_reference.py"), "--ref", ref, "--seeds", "24"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0 and lines, out.stderr[-2000:] + out.stdout[-2000:]
+    d = json.loads(lines[-1])
+    assert d["cases"] == 24 and d["failures"] == []
+    assert d["open_loop_worst"] <= 1e-10 and d["closed_loop_worst"] <= 1e-6

@@ -1,5 +1,6 @@
 """The oracle against the unmodified reference Python, live (not through fixtures): random configurations replayed in both.
-Runs only where the reference tree exists (the build container); the GPU box has the committed golden vectors instead."""
+Runs where the reference tree exists (the build container) or where its staged copy oracle/_ref does (the GPU box; the
+same check is repeated there under the gpu marker by tests/test_gpu_round2.py)."""
 import json
 import os
 import subprocess
@@ -8,7 +9,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = "/root/reference"
+# the reference tree (build container) or its staged, unmodified copy (oracle/_ref: written by __graft_entry__.build(), git-ignored,
+# travels to the GPU box)
+REF = next((r for r in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")) if os.path.isdir(os.path.join(r, "gym_pybullet_drones"))),
+           "/root/reference")
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gym_pybullet_drones")), reason="reference tree not present")
