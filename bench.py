@@ -14,8 +14,9 @@ value   = E*N*S*K / device time of EXACTLY K steps (CUDA events, max over ranks)
           ONE CUDA graph (K <= 1024; longer runs replay a 16-step graph), enqueued behind a short device-side sleep so that
           no host launch latency falls inside the event window; the window is measured `--trials` times (each bracketed by
           barrier + synchronize) and the median trial is reported, all trials listed.
-e2e     = the same metric through HoverAviary.step(numpy): pinned host action -> H2D, kernel, D2H of what the device
-          computed (kin, reward, flags: 54 B per env) into the host observation mirror (gpd_step_mirror)
+e2e     = the same metric through HoverAviary.step(numpy): pinned host actions in, what the device computed (kin, reward,
+          flags: 54 B per env) out into the host observation mirror (gpd_step_mirror); the step kernel moves both over PCIe
+          itself (mapped pinned memory) instead of separate copy operations
 roofline= algorithmic bytes (646 B per env-step) * E / kernel time, against MEASURED_PEAKS.json hbm_gbs
 other_configs = BASELINE.json configs[2..4] (C3 / C4 / C5), device-timed the same way, max over ranks
 """
@@ -728,9 +729,10 @@ def b200_arm(a):
                     "d2h_bytes_per_step_incl_window_rebuild": d2h_amortised,
                     "steps": a.e2e_steps, "ms_per_step": 1e3 * e2e_s / a.e2e_steps, "rank_s": e2e_ranks,
                     "host_obs_equals_device_obs": mirror_ok,
-                    "api": "HoverAviary.step(numpy) -> gpd_step_mirror: pinned host actions in; kin/reward/flags out into the "
-                           "pinned feature-major host observation log (the action ring is the host's own data and is never echoed); "
-                           "obs is a strided (E,1,72) view of that log"},
+                    "api": "HoverAviary.step(numpy) -> gpd_step_mirror: the step kernel reads the actions from pinned host memory and "
+                           "writes kin/reward/flags into the pinned feature-major host observation log over PCIe itself (zero-copy: "
+                           "h2d/d2h bytes are what crosses the bus every step; the action ring is the host's own data and is never "
+                           "echoed); obs is a strided (E,1,72) view of that log"},
             "gpu_launches": K,
             "roofline": roof,
             "async_pools": async_info,

@@ -76,6 +76,8 @@ struct Mirror {
     uint64_t synced_seq = 0;
     const void* synced_obs = nullptr;
     float* d_kin_t = nullptr;       // device [12][D]
+    float* d_log = nullptr;         // device alias of the pinned log (cudaHostGetDevicePointer), or nullptr
+    int zero_copy = 1;              // the step kernel reads the actions from and writes kin / reward / flags to pinned host memory itself
     float* d_full_t = nullptr;      // device [W][D], refresh scratch (lazy)
     int chunks = 1;                 // a step is issued as `chunks` launches over CTA sub-ranges, each with its own copies
     cudaStream_t cs[GPD_MIRROR_MAX_CHUNKS] = {};   // one stream per chunk: chunk c's H2D overlaps chunk c-1's kernel and D2H
@@ -678,7 +680,8 @@ int gpd_reset(gpd_sim* s, const uint8_t* env_mask, const void* obs_prev, void* o
 }
 
 static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void* obs_out, void* reward, uint8_t* terminated,
-                     uint8_t* truncated, void* terminal_kin, float* kin_t, void* stream, int64_t cta0 = 0, int64_t ncta = 0)
+                     uint8_t* truncated, void* terminal_kin, float* kin_t, void* stream, int64_t cta0 = 0, int64_t ncta = 0,
+                     int64_t kin_ld = 0, bool host_io = false)
 {
     if (!s) return fail(GPD_ERR_INVALID, "null handle");
     if (!actions || !obs_out) return fail(GPD_ERR_INVALID, "gpd_step: actions and obs_out are required");
@@ -699,7 +702,7 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
     const uintptr_t al = (uintptr_t)actions | (uintptr_t)obs_prev | (uintptr_t)obs_out;
     const uintptr_t al_out = (uintptr_t)reward | (uintptr_t)terminated | (uintptr_t)truncated;
     const bool bulk = s->bulk_ok && (al & 15) == 0;
-    const int out_plain = (al_out & 15) != 0 ? 1 : 0;
+    const int out_plain = ((al_out & 15) != 0 || host_io) ? 1 : 0;     // outputs in mapped host memory: plain stores by the threads
     LaunchCfg lc = bulk ? s->lc_bulk : s->lc;
     if (ncta > 0) lc.grid = ncta;       // a sub-range of the CTAs (chunked host-mirror step); cta0 shifts the block index
     if (s->tile_dep) {
@@ -712,14 +715,14 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         StepArgs<double> a = s->a64;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        a.kin_t = kin_t; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
+        a.kin_t = kin_t; a.kin_ld = kin_ld > 0 ? kin_ld : s->D; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
         if (bulk) CU(launch_step_bulk<double>(a, lc, st));
         else CU(launch_step<double>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     } else {
         StepArgs<float> a = s->a32;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
-        a.kin_t = kin_t; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
+        a.kin_t = kin_t; a.kin_ld = kin_ld > 0 ? kin_ld : s->D; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
         if (bulk) CU(launch_step_bulk<float>(a, lc, st));
         else CU(launch_step<float>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     }
@@ -842,7 +845,7 @@ int gpd_mirror_alloc(int64_t rows, int64_t row_len, float** log_out)
     *log_out = nullptr;
     void* p = nullptr;
     const size_t bytes = (size_t)rows * (size_t)row_len * sizeof(float);
-    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e != cudaSuccess)
         return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? GPD_ERR_NO_DEVICE : GPD_ERR_ALLOC,
                     "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
@@ -877,6 +880,12 @@ int gpd_mirror_attach(gpd_sim* s, float* log, int64_t rows, int64_t row_len, int
     Mirror& m = s->mir;
     m.log = log; m.rows = rows; m.ld = row_len; m.col0 = col0;
     m.row = 0; m.valid = false; m.pending = false;
+    {
+        void* dl = nullptr;
+        m.d_log = (cudaHostGetDevicePointer(&dl, log, 0) == cudaSuccess) ? (float*)dl : nullptr;
+        if (!m.d_log) cudaGetLastError();
+        if (const char* ev = getenv("GPD_MIRROR_ZEROCOPY")) m.zero_copy = atoi(ev) != 0;
+    }
     // Chunked issue (GPD_MIRROR_CHUNKS > 1): the step is cut into CTA sub-ranges on their own streams, so the action upload of
     // chunk c+1 can overlap the kernel of chunk c and the result download of chunk c-1 (PCIe is full duplex).  Measured through
     // the Python call site at 65,536 envs (profiles/r02): 139 / 147 / 166 / 193 us per step with 1 / 2 / 4 / 8 chunks — every
@@ -901,6 +910,17 @@ int64_t gpd_mirror_row(const gpd_sim* s)
 {
     if (!s || !s->mir.log) return fail(GPD_ERR_INVALID, "no host mirror attached");
     return s->mir.row;
+}
+
+// Device alias of a caller's host pointer when the memory is pinned and mapped (cudaHostAlloc / cudaHostRegister, e.g. torch's
+// pin_memory), else nullptr.  Asked every step (~1 us per call): a cached answer could outlive the caller's allocation.
+static void* host_alias(const void* host)
+{
+    if (!host) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) return at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
 }
 
 // device [nrows][D] (contiguous) -> log rows [row0, row0 + nrows), this handle's columns
@@ -989,7 +1009,35 @@ int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_pre
     const bool tight = z.rew_pad == z.E * z.rs && z.flag_pad == z.E;     // E % 16 == 0: the staging is [reward|term|trunc] packed
     uint8_t* d_term = (uint8_t*)(pack + z.rew_pad);
     uint8_t* d_trunc = d_term + z.flag_pad;
-    if (m.chunks <= 1) {
+    // Zero-copy step: when the caller's arrays are pinned (the facade allocates them so) the step kernel itself reads the actions
+    // from host memory and writes the 12 kin rows, reward and flags straight into the pinned log / result arrays over PCIe.
+    // One kernel launch per step instead of launch + three DMA operations, each with its own start-up latency, and the
+    // transfers run under the kernel instead of behind it.  Anything not pinned falls back to staging + copies, per array.
+    bool host_done = false;
+    if (m.chunks <= 1 && m.zero_copy && m.d_log) {
+        // [reward | terminated | truncated] in one block (the facade's layout): one look-up covers all three
+        const bool one_block = reward && (void*)terminated == (char*)reward + z.E * z.rs && truncated == terminated + z.E;
+        void* a_rew = host_alias(reward);
+        void* a_term = one_block ? (a_rew ? (char*)a_rew + z.E * z.rs : nullptr) : host_alias(terminated);
+        void* a_trunc = one_block ? (a_rew ? (char*)a_term + z.E : nullptr) : host_alias(truncated);
+        void* a_tkin = terminal_kin ? host_alias(terminal_kin) : nullptr;
+        const bool outs_ok = (!reward || a_rew) && (!terminated || a_term) && (!truncated || a_trunc) && (!terminal_kin || a_tkin);
+        if (outs_ok) {
+            const void* a_act = host_alias(actions);
+            if (!a_act) {       // pageable actions: stage them, everything else stays zero-copy
+                CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
+                a_act = s->h_act;
+            }
+            float* kin_rows = m.d_log + (m.row + s->A) * m.ld + m.col0;
+            int rc = step_impl(s, a_act, d_obs_prev, d_obs_out, a_rew, (uint8_t*)a_term, (uint8_t*)a_trunc, a_tkin, kin_rows, stream,
+                               0, 0, m.ld, true);
+            if (rc) return rc;
+            host_done = true;
+        }
+    }
+    if (host_done) {
+        // nothing to copy
+    } else if (m.chunks <= 1) {
         CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
         int rc = step_impl(s, s->h_act, d_obs_prev, d_obs_out, d_rew, d_term, d_trunc, terminal_kin ? s->h_tkin : nullptr, m.d_kin_t, stream);
         if (rc) return rc;
@@ -1020,14 +1068,16 @@ int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_pre
     if (internal) { s->h_cur = nxt; s->h_has_prev = true; }
     // reward and flags of every env (one packed copy when the caller's arrays are laid out like the staging)
     const bool packed = tight && reward && (void*)terminated == (char*)reward + z.E * z.rs && truncated == terminated + z.E;
-    if (packed) {
+    if (host_done) {
+        // written by the kernel
+    } else if (packed) {
         CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs + 2 * z.E, cudaMemcpyDeviceToHost, st));
     } else {
         if (reward) CU(cudaMemcpyAsync(reward, d_rew, z.E * z.rs, cudaMemcpyDeviceToHost, st));
         if (terminated) CU(cudaMemcpyAsync(terminated, d_term, z.E, cudaMemcpyDeviceToHost, st));
         if (truncated) CU(cudaMemcpyAsync(truncated, d_trunc, z.E, cudaMemcpyDeviceToHost, st));
     }
-    if (terminal_kin) CU(cudaMemcpyAsync(terminal_kin, s->h_tkin, (size_t)s->D * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (terminal_kin && !host_done) CU(cudaMemcpyAsync(terminal_kin, s->h_tkin, (size_t)s->D * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
     m.pending = true;
     m.pending_obs = d_obs_out;
     m.pending_actions = (const float*)actions;

@@ -103,7 +103,8 @@ struct StepArgs {
     float* terminal_kin;
     const uint8_t* reset_mask;   // reset kernel only
     unsigned long long* timeline; // diagnostics: [grid][8] phase timestamps (ns, %globaltimer) or nullptr
-    float* kin_t;           // host-mirror export: feature-major copy [12][D] of the kinematic observation part, or nullptr
+    float* kin_t;           // host-mirror export: feature-major copy [12][kin_ld] of the kinematic observation part, or nullptr
+    int64_t kin_ld;         // row stride of kin_t: D for the device staging, the log's row length when the rows ARE the pinned host log
     unsigned long long* tile_seq;   // per-CTA step sequencing, one 64-bit word per tile at a 32-byte stride (tile_claim_and_wait)
     int32_t tile_dep;       // 1: a CTA waits only for ITS OWN tile's previous step (per-CTA flag) instead of the whole grid
     int32_t target_per_env; // 1: p.target holds D entries (per-env MultiHover targets), else N

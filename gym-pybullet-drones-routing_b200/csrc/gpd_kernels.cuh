@@ -733,7 +733,7 @@ step_kernel(const __grid_constant__ StepArgs<R> a, const __grid_constant__ CUten
 
     if (a.kin_t && active && !ctrl) {   // host mirror (gpd_step_mirror): feature-major copy of the kin part, coalesced per feature
 #pragma unroll
-        for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.D + d] = kin[k];
+        for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.kin_ld + d] = kin[k];
     }
 
     // ---- stage this drone's observation row in shared memory ----

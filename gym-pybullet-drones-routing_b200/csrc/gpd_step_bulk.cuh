@@ -317,7 +317,7 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
         }
         if (a.kin_t) {                      // host mirror: feature-major copy of the kin part
 #pragma unroll
-            for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.D + d] = kin[k];
+            for (int k = 0; k < 12; ++k) a.kin_t[(int64_t)k * a.kin_ld + d] = kin[k];
         }
     }
 }

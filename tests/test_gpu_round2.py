@@ -34,29 +34,40 @@ def _kw(env_kind="hover", act="rpm", N=1, freq=30, flags=0, model=DroneModel.CF2
                 init_xyz=None, init_rpy=None)
 
 
-@pytest.mark.parametrize("act,N,freq,precision,chunks", [("rpm", 1, 30, "f32", 1), ("rpm", 1, 30, "f32", 3), ("rpm", 1, 48, "f64", 1),
-                                                           ("pid", 1, 48, "f32", 4), ("one_d_rpm", 1, 30, "f32", 1),
-                                                           ("rpm", 3, 30, "f32", 2), ("vel", 2, 30, "f64", 1)])
-def test_cuda_host_mirror_equals_device_observation(act, N, freq, precision, chunks, monkeypatch):
+@pytest.mark.parametrize("act,N,freq,precision,chunks,io", [
+    ("rpm", 1, 30, "f32", 1, "zc"), ("rpm", 1, 30, "f32", 3, "zc"), ("rpm", 1, 48, "f64", 1, "zc"), ("pid", 1, 48, "f32", 4, "zc"),
+    ("one_d_rpm", 1, 30, "f32", 1, "zc"), ("rpm", 3, 30, "f32", 2, "zc"), ("vel", 2, 30, "f64", 1, "zc"),
+    ("rpm", 1, 30, "f32", 1, "zc_pinned_actions"), ("pid", 1, 48, "f64", 1, "zc_pinned_actions"), ("rpm", 2, 30, "f32", 1, "zc_pinned_actions"),
+    ("rpm", 1, 30, "f32", 1, "dma"), ("vel", 2, 30, "f64", 1, "dma"), ("rpm", 1, 30, "f32", 1, "pageable_outputs")])
+def test_cuda_host_mirror_equals_device_observation(act, N, freq, precision, chunks, io, monkeypatch):
     """The numpy-facing step returns a strided view of the pinned feature-major log; at every step it must equal, bit for bit,
     the device observation (same chain), through window slides, compactions (16-step log), masked and full resets, and
     tensor-path steps in between (stale mirror -> rebuilt); also when the step is issued in chunks over CTA sub-ranges
-    (each with its own copies on its own stream, the default from 32,768 drones)."""
+    (each with its own copies on its own stream).  io: "zc" = the zero-copy step (one chunk, pinned result arrays: the kernel
+    writes kin rows / reward / flags / terminal rows straight into host memory; pageable actions are staged),
+    "zc_pinned_actions" = it also reads the actions from host memory, "dma" = GPD_MIRROR_ZEROCOPY=0 (staging + copies),
+    "pageable_outputs" = result arrays the device cannot address (falls back to staging + copies by itself)."""
     rng = np.random.default_rng(3)
     E = 517
     monkeypatch.setenv("GPD_MIRROR_CHUNKS", str(chunks))
+    if io == "dma":
+        monkeypatch.setenv("GPD_MIRROR_ZEROCOPY", "0")
     kw = _kw("hover" if N == 1 else "multihover", act, N, freq, model=DroneModel.CF2P if act in ("pid", "vel") else DroneModel.CF2X)
     sim = make_sim(kw, E, precision, auto_reset=True)
     twin = make_sim(kw, E, precision, auto_reset=True)      # the same run on device tensors only
     sim.attach_mirror(slide_steps=16)
     A = sim.A
-    out = sim.alloc_host_outputs(pinned=True, terminal_kin=True)
+    out = sim.alloc_host_outputs(pinned=io != "pageable_outputs", terminal_kin=True)
+    pinned_a = torch.empty((E, N, A), dtype=torch.float32).pin_memory().numpy() if io == "zc_pinned_actions" else None
     obs = sim.reset_host()
     twin.reset()
     assert obs.shape == (E, N, sim.W) and obs.dtype == np.float32 and not obs.flags["C_CONTIGUOUS"]
     assert np.array_equal(obs, sim.obs.cpu().numpy()) and np.array_equal(obs, twin.obs.cpu().numpy())
     for t in range(70):
         a = rng.uniform(-1, 1, (E, N, A)).astype(np.float32)
+        if pinned_a is not None:
+            pinned_a[...] = a
+            a = pinned_a
         od, rd, td, trd = twin.step(torch.from_numpy(a).cuda())
         if t in (23, 24, 40):               # tensor-path steps: the device chain moves without the mirror
             sim.step(torch.from_numpy(a).cuda())
