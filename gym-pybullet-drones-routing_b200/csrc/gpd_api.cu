@@ -176,20 +176,40 @@ static cudaError_t use_device(int dev)
 // statistics, ...) breaks the chain, so the step that follows is fully ordered behind it.  Work enqueued by others is the
 // caller's side of the contract.
 struct ChainTable {
+    struct Entry { bool last_was_step; unsigned long long capture; };   // capture = id of the stream capture the launch belonged to (0: none)
     std::mutex mu;
-    std::unordered_map<unsigned long long, bool> last_was_step;
+    std::unordered_map<unsigned long long, Entry> tab;
     static unsigned long long key(int dev, cudaStream_t st) { return ((unsigned long long)(uintptr_t)st << 6) ^ (unsigned long long)dev; }
-    bool get(int dev, cudaStream_t st) { std::lock_guard<std::mutex> l(mu); auto it = last_was_step.find(key(dev, st)); return it != last_was_step.end() && it->second; }
-    void set(int dev, cudaStream_t st, bool v) { std::lock_guard<std::mutex> l(mu); last_was_step[key(dev, st)] = v; }
-    void clear() { std::lock_guard<std::mutex> l(mu); last_was_step.clear(); }
+    bool get(int dev, cudaStream_t st, unsigned long long capture)
+    {
+        std::lock_guard<std::mutex> l(mu);
+        auto it = tab.find(key(dev, st));
+        return it != tab.end() && it->second.last_was_step && it->second.capture == capture;
+    }
+    void set(int dev, cudaStream_t st, bool v, unsigned long long capture)
+    {
+        std::lock_guard<std::mutex> l(mu);
+        if (tab.size() > 4096) tab.clear();      // stream handles come and go; forgetting one only costs one unchained launch
+        tab[key(dev, st)] = Entry{ v, capture };
+    }
+    void clear() { std::lock_guard<std::mutex> l(mu); tab.clear(); }
 };
+// A step captured into a CUDA graph chains only behind a step of the SAME capture (a stream handle is reused across captures
+// and eager work; a graph's first kernel must not claim a predecessor it does not have).
+static unsigned long long capture_id(cudaStream_t st)
+{
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(st, &status, &id) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return status == cudaStreamCaptureStatusActive ? id : 0;
+}
 static ChainTable g_chain;
 // a launch on `st` that is not a step kernel; calls without a stream of their own (synchronous uploads) break every chain
 static inline void unchain(gpd_sim* s, void* stream = nullptr, bool all = false)
 {
     if (!s) return;
     if (all) g_chain.clear();
-    else g_chain.set(s->cfg.device, (cudaStream_t)stream, false);
+    else g_chain.set(s->cfg.device, (cudaStream_t)stream, false, 0);
 }
 
 static int action_width(int act)
@@ -709,7 +729,7 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         // programmatic launch only when the caller opted in (gpd_set_step_chaining) and the library's previous launch on this
         // stream was a step kernel; otherwise plain stream order (the kernel still claims / publishes its tiles, so a
         // chained successor sequences correctly behind it)
-        lc.pdl = (s->chaining && lc.pdl && g_chain.get(s->cfg.device, st)) ? 1 : 0;
+        lc.pdl = (s->chaining && lc.pdl && g_chain.get(s->cfg.device, st, capture_id(st))) ? 1 : 0;
     }
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
@@ -730,7 +750,7 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         s->last_obs = obs_out;
         ++s->obs_seq;
     }
-    g_chain.set(s->cfg.device, st, true);
+    g_chain.set(s->cfg.device, st, true, capture_id(st));
     return GPD_OK;
 }
 

@@ -452,3 +452,45 @@ def test_oracle_matches_the_staged_reference_on_this_box():
     d = json.loads(lines[-1])
     assert d["cases"] == 24 and d["failures"] == []
     assert d["open_loop_worst"] <= 1e-10 and d["closed_loop_worst"] <= 1e-6
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_cuda_chained_stepping_across_eager_and_captured_launches(precision):
+    """gpd_set_step_chaining on one stream handle that carries, in turn, eager steps, a CUDA-graph capture, replays of that
+    graph, a reset and more eager steps: a step chains only behind a step kernel of the same capture (or of eager work), never
+    behind the library's own reset, and the results equal unchained stepping bit for bit."""
+    rng = np.random.default_rng(21)
+    E = 20000
+    kw = _kw()
+    chained, plain = make_sim(kw, E, precision, auto_reset=True), make_sim(kw, E, precision, auto_reset=True)
+    chained.set_step_chaining(True)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)).cuda() for _ in range(4)]
+    side = torch.cuda.Stream()
+    outs = []
+    for sim in (chained, plain):
+        sim.reset()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for k in range(3):
+                sim.step(acts[k % 4])                    # eager on the stream the capture will use
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for k in range(6):                       # even count: the observation ping-pong is back where it started
+                    sim.step(acts[k % 4])
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            sim.step(acts[1])
+            m = torch.from_numpy((rng.random(E) < 0.5).astype(np.uint8)).cuda() if sim is chained else m
+            sim.reset(m)                                 # the library's own kernel breaks the chain
+            sim.step(acts[2]); sim.step(acts[3])
+        torch.cuda.synchronize()
+        outs.append([x.clone() for x in sim.get_state()] + [sim.obs.clone(), sim.reward.clone(), torch.from_numpy(sim.episode_stats())])
+    for x, y in zip(*outs):
+        xi = x.contiguous().view(torch.int64 if x.element_size() == 8 else (torch.int32 if x.element_size() == 4 else torch.uint8))
+        yi = y.contiguous().view(xi.dtype)
+        assert torch.equal(xi, yi)
+    chained.close(); plain.close()
