@@ -1048,6 +1048,9 @@ int gpd_step_mirror_begin(gpd_sim* s, const void* actions, const void* d_obs_pre
                 CU(cudaMemcpyAsync(s->h_act, actions, z.act_b, cudaMemcpyHostToDevice, st));
                 a_act = s->h_act;
             }
+            // Measured alternatives (profiles/r02/e2e_breakdown.jsonl): staging the actions with a DMA copy and keeping only the
+            // outputs zero-copy 121 us of device time, kin rows by one DMA copy behind the kernel 110 us, everything by the
+            // kernel 105 us (the link delivers ~42 GB/s device-to-host on this pool: 3.5 MB = 84 us is the floor)
             float* kin_rows = m.d_log + (m.row + s->A) * m.ld + m.col0;
             int rc = step_impl(s, a_act, d_obs_prev, d_obs_out, a_rew, (uint8_t*)a_term, (uint8_t*)a_trunc, a_tkin, kin_rows, stream,
                                0, 0, m.ld, true);

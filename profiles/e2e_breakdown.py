@@ -22,6 +22,8 @@ rng = np.random.default_rng(0)
 for p in pin:
     p.copy_(torch.from_numpy(rng.uniform(-1, 1, (E, 1, 4)).astype(np.float32)))
 acts = [p.numpy() for p in pin]
+if os.environ.get("PAGEABLE_ACTIONS"):      # the library then stages the actions with a DMA copy and keeps zero-copy outputs
+    acts = [np.array(a) for a in acts]
 out = sim.alloc_host_outputs(pinned=True)
 for k in range(20):
     sim.step_host(acts[k % 4], out)
@@ -56,5 +58,5 @@ for k in range(50):
     sim.step_host_end()
     torch.cuda.synchronize()
     dev += e0.elapsed_time(e1)
-print(json.dumps({"E": E, "zero_copy": os.environ.get("GPD_MIRROR_ZEROCOPY", "1"), "begin_us": 1e6 * tb / n, "end_us": 1e6 * te / n,
+print(json.dumps({"E": E, "zero_copy": os.environ.get("GPD_MIRROR_ZEROCOPY", "1"), "pageable_actions": bool(os.environ.get("PAGEABLE_ACTIONS")), "begin_us": 1e6 * tb / n, "end_us": 1e6 * te / n,
                   "end_host_only_us": 1e6 * tw / 50, "facade_step_us": 1e6 * tf / n, "device_us": 1e3 * dev / 50}))
