@@ -102,6 +102,7 @@ struct gpd_sim {
     bool bulk_ok = false;             // single-drone RL env with 4-wide actions: the bulk-copy data path (gpd_step_bulk.cuh)
     LaunchCfg lc_bulk{};
     int bulk_direct = 0;              // BulkSmem::direct
+    int bulk_tpc = 1;                 // tiles per CTA of chained bulk launches
     int64_t d_pad = 0;                // per-env scalar arrays are allocated for whole tiles (grid * DPB entries)
     const void* last_obs = nullptr;   // the observation buffer most recently written by gpd_step / gpd_reset (device)
     uint64_t obs_seq = 0;             // bumped whenever the device observation chain advances (or is replaced by the caller)
@@ -176,21 +177,23 @@ static cudaError_t use_device(int dev)
 // statistics, ...) breaks the chain, so the step that follows is fully ordered behind it.  Work enqueued by others is the
 // caller's side of the contract.
 struct ChainTable {
-    struct Entry { bool last_was_step; unsigned long long capture; };   // capture = id of the stream capture the launch belonged to (0: none)
+    struct Entry { bool last_was_step; unsigned long long capture; const void* sim; };   // capture = id of the stream capture the launch
+                                                                                         // belonged to (0: none); sim = its handle
     std::mutex mu;
     std::unordered_map<unsigned long long, Entry> tab;
     static unsigned long long key(int dev, cudaStream_t st) { return ((unsigned long long)(uintptr_t)st << 6) ^ (unsigned long long)dev; }
-    bool get(int dev, cudaStream_t st, unsigned long long capture)
+    bool get(int dev, cudaStream_t st, unsigned long long capture, const void** last_sim = nullptr)
     {
         std::lock_guard<std::mutex> l(mu);
         auto it = tab.find(key(dev, st));
+        if (last_sim) *last_sim = it != tab.end() ? it->second.sim : nullptr;
         return it != tab.end() && it->second.last_was_step && it->second.capture == capture;
     }
-    void set(int dev, cudaStream_t st, bool v, unsigned long long capture)
+    void set(int dev, cudaStream_t st, bool v, unsigned long long capture, const void* sim = nullptr)
     {
         std::lock_guard<std::mutex> l(mu);
         if (tab.size() > 4096) tab.clear();      // stream handles come and go; forgetting one only costs one unchained launch
-        tab[key(dev, st)] = Entry{ v, capture };
+        tab[key(dev, st)] = Entry{ v, capture, sim };
     }
     void clear() { std::lock_guard<std::mutex> l(mu); tab.clear(); }
 };
@@ -525,6 +528,10 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     const bool lean = rpm_like && cfg->physics_flags == 0;
     int P0 = 64;
     if (N == 1) P0 = (A == 4 && (f64 || !lean)) ? 128 : 64;      // A < 4: the 32 funnel-copy lanes limit the tile to 64 rows
+    // lean FP32 sims on the bulk kernel: 128-env tiles in the range where launches are sequenced per tile and still give every SM
+    // two CTAs of two tiles each (profiles/r02/sweep_b14/b16.jsonl, two tiles per CTA: 65,536 envs 7.74 us with 128-env tiles,
+    // 8.12 us with 64; 16,384 envs 3.42 vs 3.28 us; 262,144 envs equal; 524,288 envs 68.4 vs 65.5 us, 1 M envs 124.6 vs 121.9 us)
+    if (N == 1 && A == 4 && !f64 && lean && !ctrl && s->D >= 4 * 148 * 64 && s->D <= 262144) P0 = 128;
     else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 64 : 224;     // downwash: two block barriers per substep favour small CTAs
                                                                 // (512 envs x 64 drones: 17.4 us at 64 threads, 24.1 at 128)
     Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0);
@@ -586,6 +593,9 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         int direct = 2;
         if (const char* dv = getenv("GPD_BULK_DIRECT")) direct = atoi(dv) < 0 ? 0 : (atoi(dv) > 2 ? 2 : atoi(dv));
         s->bulk_direct = direct;
+        // two tiles per CTA for chained FP32 launches that still leave >= 1.5 CTAs per SM (FP64: 13.2 us with one tile, 13.9 with two)
+        s->bulk_tpc = (!f64 && L.grid >= 3 * 148) ? 2 : 1;
+        if (const char* tv = getenv("GPD_BULK_TPC")) s->bulk_tpc = atoi(tv) < 1 ? 1 : (atoi(tv) > GPD_BULK_MAX_TPC ? GPD_BULK_MAX_TPC : atoi(tv));
         const size_t bsm = (size_t)DPB * s->W * 4 + (direct >= 2 ? 0 : 3 * (size_t)DPB * 4 * rs) +
                            (direct ? 0 : (size_t)DPB * 16 + 2 * (size_t)DPB * rs + 2 * (size_t)DPB * 4 + 2 * (size_t)DPB) + 8 * 32;
         // Eligible: single-drone RL env, 4-wide actions, whole-float4 rows, 16-row-aligned tiles that fit shared memory.
@@ -725,17 +735,31 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
     const int out_plain = ((al_out & 15) != 0 || host_io) ? 1 : 0;     // outputs in mapped host memory: plain stores by the threads
     LaunchCfg lc = bulk ? s->lc_bulk : s->lc;
     if (ncta > 0) lc.grid = ncta;       // a sub-range of the CTAs (chunked host-mirror step); cta0 shifts the block index
+    const void* prev_sim = nullptr;     // handle of the step kernel this one is chained behind
     if (s->tile_dep) {
         // programmatic launch only when the caller opted in (gpd_set_step_chaining) and the library's previous launch on this
         // stream was a step kernel; otherwise plain stream order (the kernel still claims / publishes its tiles, so a
         // chained successor sequences correctly behind it)
-        lc.pdl = (s->chaining && lc.pdl && g_chain.get(s->cfg.device, st, capture_id(st))) ? 1 : 0;
+        lc.pdl = (s->chaining && lc.pdl && g_chain.get(s->cfg.device, st, capture_id(st), &prev_sim)) ? 1 : 0;
     }
+    // tiles of this launch and tiles per CTA (bulk kernel).  A launch chained behind a step of ANOTHER handle (independent env
+    // sets in rotation) folds bulk_tpc tiles into one CTA (one buffer, claims up front, a tile published under the next tile's
+    // loads: gpd_step_bulk.cuh): 8.6 -> 7.7 us per 65,536-env step.  One tile per CTA otherwise: alone on the machine a grid of
+    // fewer, longer CTAs is only slower, and behind a step of the SAME handle the tiles depend on each other one to one, so the
+    // finer grain overlaps better (7.1 vs 8.5 us).  The per-tile words make the two mappings interchangeable.
+    const int64_t tiles = lc.grid;
+    int tpc = 1;
+    if (bulk && s->tile_dep && lc.pdl && ncta == 0 && s->bulk_tpc > 1 && prev_sim != (const void*)s) {
+        tpc = s->bulk_tpc;
+        lc.grid = (tiles + tpc - 1) / tpc;
+    }
+    const bool last_chunk = cta0 + tiles >= s->lc.grid;
     if (s->cfg.precision == GPD_F64) {
         StepArgs<double> a = s->a64;
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (double*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
         a.kin_t = kin_t; a.kin_ld = kin_ld > 0 ? kin_ld : s->D; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
+        a.tpc = tpc; a.tile_end = (int32_t)(cta0 + tiles);
         if (bulk) CU(launch_step_bulk<double>(a, lc, st));
         else CU(launch_step<double>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     } else {
@@ -743,14 +767,15 @@ static int step_impl(gpd_sim* s, const void* actions, const void* obs_prev, void
         a.actions = actions; a.obs_prev = (const float*)obs_prev; a.obs_out = obs_out; a.reward = (float*)reward;
         a.terminated = terminated; a.truncated = truncated; a.terminal_kin = (float*)terminal_kin; a.use_tma = use_tma;
         a.kin_t = kin_t; a.kin_ld = kin_ld > 0 ? kin_ld : s->D; a.cta0 = (int32_t)cta0; a.out_plain = out_plain;
+        a.tpc = tpc; a.tile_end = (int32_t)(cta0 + tiles);
         if (bulk) CU(launch_step_bulk<float>(a, lc, st));
         else CU(launch_step<float>(a, lc, have ? &tp : nullptr, have ? &to : nullptr, have && s->tma_edge ? &te : nullptr, st));
     }
-    if (cta0 + lc.grid >= s->lc.grid) {   // the launch that covers the last CTA completes the step
+    if (last_chunk) {                     // the launch that covers the last CTA completes the step
         s->last_obs = obs_out;
         ++s->obs_seq;
     }
-    g_chain.set(s->cfg.device, st, true, capture_id(st));
+    g_chain.set(s->cfg.device, st, true, capture_id(st), s);
     return GPD_OK;
 }
 

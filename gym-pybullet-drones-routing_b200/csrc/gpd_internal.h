@@ -9,7 +9,7 @@
 
 namespace gpd {
 
-enum { GPD_MAX_DEVICES = 64 };
+enum { GPD_MAX_DEVICES = 64, GPD_BULK_MAX_TPC = 2 };
 
 // per-block episode-statistics partials: sums {episodes, return, length, return^2, env_steps, terminated} and the
 // min/max episode return as order-preserving int32 images of float32
@@ -110,6 +110,8 @@ struct StepArgs {
     int32_t target_per_env; // 1: p.target holds D entries (per-env MultiHover targets), else N
     int32_t cta0;           // first CTA of this launch (0 unless the step is issued in chunks)
     int32_t out_plain;      // bulk path, per call: reward / terminated / truncated are not all 16-byte aligned -> plain stores by the threads
+    int32_t tpc;            // bulk path, per call: tiles per CTA (0/1 = one; chained launches may take GPD_BULK_MAX_TPC)
+    int32_t tile_end;       // bulk path, per call: first tile not covered by this launch
     int32_t bulk_direct;    // bulk path: what bypasses shared memory (0 nothing, 1 the small per-env arrays, 2 the state vectors too)
     SimPtrs<R> p;
     DevDrone<R> drone;

@@ -44,22 +44,28 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 //           (pending == 0), that its predecessor has published — the acquire side makes the predecessor's tile visible;
 // publish = red.release.add -1 (borrows nothing: pending >= 1 while this CTA is alive).
 // A CTA that found predecessors pending polls until pending - 1 - (claims made after its own) == 0.
-__device__ __forceinline__ void tile_claim_and_wait(unsigned long long* w)
+// claim: returns the old word (several claims may be in flight at once: nothing waits here)
+__device__ __forceinline__ unsigned long long tile_claim(unsigned long long* w)
 {
     unsigned long long old;
     // acquire only: a claiming CTA has written nothing yet (an acq_rel atomic would put MEMBAR.ALL.GPU + ERRBAR in front, ~1 us)
     asm volatile("atom.acquire.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(w), "l"(0x100000001ull) : "memory");
-    if ((uint32_t)old != 0u) {
-        const uint32_t mine = (uint32_t)(old >> 32);
-        for (;;) {
-            unsigned long long cur;
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(w) : "memory");
-            const uint32_t later = (uint32_t)(cur >> 32) - mine - 1u;      // claims made after this one
-            if ((uint32_t)cur - 1u - later == 0u) break;
-            __nanosleep(32);
-        }
+    return old;
+}
+// wait until every step claimed before `old`'s claim has published
+__device__ __forceinline__ void tile_wait(unsigned long long* w, unsigned long long old)
+{
+    if ((uint32_t)old == 0u) return;
+    const uint32_t mine = (uint32_t)(old >> 32);
+    for (;;) {
+        unsigned long long cur;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(w) : "memory");
+        const uint32_t later = (uint32_t)(cur >> 32) - mine - 1u;      // claims made after this one
+        if ((uint32_t)cur - 1u - later == 0u) break;
+        __nanosleep(32);
     }
 }
+__device__ __forceinline__ void tile_claim_and_wait(unsigned long long* w) { tile_wait(w, tile_claim(w)); }
 __device__ __forceinline__ void tile_publish(unsigned long long* w)
 {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(w), "l"(0xffffffffffffffffull) : "memory");

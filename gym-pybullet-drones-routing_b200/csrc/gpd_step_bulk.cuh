@@ -353,26 +353,42 @@ __device__ __forceinline__ void bulk_tile_stats(const StepArgs<R>& a, const Bulk
 }
 
 template <typename R, int KIND>
-// registers: FP32 lean 64 (8 CTAs of 128 threads), DSLPID 72, force models 80; FP64 128 — shared memory (26-53 KB per tile)
+// registers: FP32 lean 64 (8 CTAs of 128 threads), DSLPID 80 (72 spilled once the tile loop was added), force models 80; FP64 128 — shared memory (26-53 KB per tile)
 // caps the FP64 variants at 512 threads per SM anyway, so they get the registers that would otherwise spill
-__global__ void __launch_bounds__(128, sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 8 : (KIND == GPD_K_PID ? 7 : 5)) : 4)
+__global__ void __launch_bounds__(128, sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 8 : (KIND == GPD_K_PID ? 6 : 5)) : 4)
 step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const int t = threadIdx.x;
-    const int bid = (int)blockIdx.x + a.cta0;
     const int T = a.DPB;
     const int direct = a.bulk_direct;
     BulkSmem<R> sm{ smem_raw, T, a.W, direct };
-    const int64_t row0 = (int64_t)bid * T;
-    const int rows = (int)min((int64_t)T, a.D - row0);
-    const bool full = rows == T;
+    // Tiles of this CTA: one by default.  A chained launch (gpd_set_step_chaining) gives every CTA up to `tpc` tiles, strided by
+    // the grid so that at any moment the CTAs cover a contiguous range: the tiles run one after the other through the SAME
+    // shared-memory buffer, all claims are issued up front in one round trip, and a tile is published while the NEXT tile's
+    // loads are in flight: its store drain and its release fence no longer hold the buffer idle (a buffer is busy from load
+    // issue to store read, not from claim to publish), and a dependent step still sees each tile as soon as it is complete.
+    const int tpc = a.tpc > 0 ? a.tpc : 1;
+    const int tile_end = a.tile_end;        // first tile NOT covered by this launch
+    const int tile0 = (int)blockIdx.x + a.cta0;
 
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 0] = gtime();
+    if (a.timeline && t == 0) a.timeline[(int64_t)tile0 * 8 + 0] = gtime();
     if (t == 0) mbar_init(&bar, 1);
+    unsigned long long claimed[GPD_BULK_MAX_TPC];
     if (a.tile_dep) {
-        if (t == 0) tile_claim_and_wait(a.tile_seq + (int64_t)bid * 4);
+        if (t == 0) {
+            unsigned pend_any = 0;
+#pragma unroll
+            for (int it = 0; it < GPD_BULK_MAX_TPC; ++it) {
+                claimed[it] = 0;
+                const int tile = tile0 + it * (int)gridDim.x;
+                if (it < tpc && tile < tile_end) claimed[it] = tile_claim(a.tile_seq + (int64_t)tile * 4);
+            }
+#pragma unroll
+            for (int it = 0; it < GPD_BULK_MAX_TPC; ++it) pend_any |= (unsigned)claimed[it];     // every claim is performed
+            if (pend_any) tile_wait(a.tile_seq + (int64_t)tile0 * 4, claimed[0]);               // the first tile's predecessors
+        }
         __syncthreads();
         if (a.pdl_trigger_early) pdl_launch_dependents();
     } else {
@@ -380,93 +396,128 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
         __syncthreads();
         pdl_wait();
     }
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 1] = gtime();
+    if (a.timeline && t == 0) a.timeline[(int64_t)tile0 * 8 + 1] = gtime();
 
-    // ---- loads: everything this tile needs, in flight at once ----
+#pragma unroll 1
+    for (int it = 0; it < tpc; ++it) {
+        const int bid = tile0 + it * (int)gridDim.x;
+        if (bid >= tile_end) break;             // uniform over the CTA
+        const int64_t row0 = (int64_t)bid * T;
+        const int rows = (int)min((int64_t)T, a.D - row0);
+        const bool full = rows == T;
+        if (it > 0) {
+            if (t == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores have read the buffer
+                if (a.tile_dep) {
+#pragma unroll
+                    for (int k = 1; k < GPD_BULK_MAX_TPC; ++k)
+                        if (k == it && (unsigned)claimed[k]) tile_wait(a.tile_seq + (int64_t)bid * 4, claimed[k]);
+                }
+                if (a.timeline) { a.timeline[(int64_t)bid * 8 + 0] = gtime(); a.timeline[(int64_t)bid * 8 + 1] = gtime(); }
+            }
+            __syncthreads();                    // buffer free, this tile's previous step visible
+        }
+
+        // ---- loads: everything this tile needs, in flight at once ----
+        if (t == 0) {
+            fence_proxy_async_global();         // generic-proxy writes of the tile's previous step (ragged tails) -> bulk reads
+            const uint32_t v4b = (uint32_t)sizeof(V4<R>);
+            // A == 4: read at +A floats (already shifted); the last tile of the buffer must not read past its end: its final row
+            // loses the 16 stray bytes.  A < 4: whole rows, unshifted (slide_row)
+            const uint32_t shift = a.A == 4 ? 4u : 0u;
+            const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((shift && row0 + rows >= a.D) ? 16u : 0u) : 0u;
+            const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
+            const uint32_t total = ob + (direct >= 2 ? 0u : 3 * st) + (direct ? 0u : (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u));
+            mbar_expect_tx(&bar, total);
+            if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + shift, ob, &bar);
+            if (direct < 2) {
+                bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
+                bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
+                bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
+            }
+            if (!direct) {
+                bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
+                bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);              // library arrays are padded to whole tiles
+                bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
+                if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
+            }
+        }
+        BulkPre<R> pre;
+        pre.act = make_float4(0.f, 0.f, 0.f, 0.f); pre.wz = R(0); pre.cnt = 0; pre.ep = 0.f;
+        pre.p4 = pre.q4 = pre.v4 = M<R>::make4(R(0), R(0), R(0), R(0));
+        if (direct && t < rows) {               // the thread's own small inputs: in flight under the bulk loads
+            const int64_t d = row0 + t;
+            if (a.A == 4) {
+                pre.act = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
+            } else {
+                const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
+                pre.act.x = __ldg(ap);
+                if (a.A > 1) pre.act.y = __ldg(ap + 1);
+                if (a.A > 2) pre.act.z = __ldg(ap + 2);
+            }
+            pre.wz = a.p.sWz[d];
+            pre.cnt = a.p.counter[d];
+            if (a.auto_reset) pre.ep = a.p.ep_ret[d];
+            if (direct >= 2) { pre.p4 = a.p.sP[d]; pre.q4 = a.p.sQ[d]; pre.v4 = a.p.sV[d]; }
+        }
+        if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
+            float* r = sm.obs() + (size_t)t * a.W;
+            for (int k = 12; k < a.W; ++k) r[k] = 0.f;
+        }
+        if (it > 0 && t == 0 && a.tile_dep) {   // the previous tile: its stores drain and its release fence runs under THIS tile's loads
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            const int prev = bid - (int)gridDim.x;
+            tile_publish(a.tile_seq + (int64_t)prev * 4);
+            if (a.timeline) a.timeline[(int64_t)prev * 8 + 7] = gtime();
+        }
+        mbar_wait(&bar, (uint32_t)(it & 1));
+        if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
+
+        bulk_tile_physics<R, KIND>(a, sm, pre, t, row0, rows, bid);
+        fence_proxy_async_smem();               // this thread's shared-memory writes -> the bulk stores below
+        __syncthreads();
+        if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();
+
+        if (t == 0) {
+            const uint32_t v4b = (uint32_t)sizeof(V4<R>);
+            const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
+            bulk_s2g(reinterpret_cast<float*>(a.obs_out) + row0 * a.W, sm.obs(), (uint32_t)rows * a.W * 4);
+            if (direct < 2) {
+                bulk_s2g(a.p.sP + row0, sm.sP(), st);
+                bulk_s2g(a.p.sQ + row0, sm.sQ(), st);
+                bulk_s2g(a.p.sV + row0, sm.sV(), st);
+            }
+            if (!direct) {
+                bulk_s2g(a.p.sWz + row0, sm.sWz(), sc);
+                bulk_s2g(a.p.counter + row0, sm.cnt(), i4);
+                if (a.auto_reset) bulk_s2g(a.p.ep_ret + row0, sm.ep(), i4);
+            }
+            if (full && !direct && !a.out_plain) {
+                if (a.reward) bulk_s2g(a.reward + row0, sm.rew(), sc);
+                if (a.terminated) bulk_s2g(a.terminated + row0, sm.term(), (uint32_t)T);
+                if (a.truncated) bulk_s2g(a.truncated + row0, sm.trunc(), (uint32_t)T);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            bulk_tile_stats<R>(a, sm, bid, rows);
+        }
+    }
+
     if (t == 0) {
-        fence_proxy_async_global();         // generic-proxy writes of the tile's previous step (ragged tails) -> bulk reads
-        const uint32_t v4b = (uint32_t)sizeof(V4<R>);
-        // A == 4: read at +A floats (already shifted); the last tile of the buffer must not read past its end: its final row
-        // loses the 16 stray bytes.  A < 4: whole rows, unshifted (slide_row)
-        const uint32_t shift = a.A == 4 ? 4u : 0u;
-        const uint32_t ob = a.obs_prev ? (uint32_t)rows * a.W * 4 - ((shift && row0 + rows >= a.D) ? 16u : 0u) : 0u;
-        const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
-        const uint32_t total = ob + (direct >= 2 ? 0u : 3 * st) + (direct ? 0u : (uint32_t)rows * 16u + sc + i4 + (a.auto_reset ? i4 : 0u));
-        mbar_expect_tx(&bar, total);
-        if (ob) bulk_g2s(sm.obs(), a.obs_prev + row0 * a.W + shift, ob, &bar);
-        if (direct < 2) {
-            bulk_g2s(sm.sP(), a.p.sP + row0, st, &bar);
-            bulk_g2s(sm.sQ(), a.p.sQ + row0, st, &bar);
-            bulk_g2s(sm.sV(), a.p.sV + row0, st, &bar);
-        }
-        if (!direct) {
-            bulk_g2s(sm.act(), reinterpret_cast<const float4*>(a.actions) + row0, (uint32_t)rows * 16u, &bar);
-            bulk_g2s(sm.sWz(), a.p.sWz + row0, sc, &bar);              // library arrays are padded to whole tiles
-            bulk_g2s(sm.cnt(), a.p.counter + row0, i4, &bar);
-            if (a.auto_reset) bulk_g2s(sm.ep(), a.p.ep_ret + row0, i4, &bar);
-        }
-    }
-    BulkPre<R> pre;
-    pre.act = make_float4(0.f, 0.f, 0.f, 0.f); pre.wz = R(0); pre.cnt = 0; pre.ep = 0.f;
-    pre.p4 = pre.q4 = pre.v4 = M<R>::make4(R(0), R(0), R(0), R(0));
-    if (direct && t < rows) {               // the thread's own small inputs: in flight under the bulk loads
-        const int64_t d = row0 + t;
-        if (a.A == 4) {
-            pre.act = __ldg(reinterpret_cast<const float4*>(a.actions) + d);
-        } else {
-            const float* ap = reinterpret_cast<const float*>(a.actions) + d * a.A;
-            pre.act.x = __ldg(ap);
-            if (a.A > 1) pre.act.y = __ldg(ap + 1);
-            if (a.A > 2) pre.act.z = __ldg(ap + 2);
-        }
-        pre.wz = a.p.sWz[d];
-        pre.cnt = a.p.counter[d];
-        if (a.auto_reset) pre.ep = a.p.ep_ret[d];
-        if (direct >= 2) { pre.p4 = a.p.sP[d]; pre.q4 = a.p.sQ[d]; pre.v4 = a.p.sV[d]; }
-    }
-    if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
-        float* r = sm.obs() + (size_t)t * a.W;
-        for (int k = 12; k < a.W; ++k) r[k] = 0.f;
-    }
-    mbar_wait(&bar, 0);
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
-
-    bulk_tile_physics<R, KIND>(a, sm, pre, t, row0, rows, bid);
-    fence_proxy_async_smem();               // this thread's shared-memory writes -> the bulk stores below
-    __syncthreads();
-    if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();
-
-    if (t == 0) {
-        const uint32_t v4b = (uint32_t)sizeof(V4<R>);
-        const uint32_t st = (uint32_t)rows * v4b, sc = (uint32_t)T * (uint32_t)sizeof(R), i4 = (uint32_t)T * 4u;
-        bulk_s2g(reinterpret_cast<float*>(a.obs_out) + row0 * a.W, sm.obs(), (uint32_t)rows * a.W * 4);
-        if (direct < 2) {
-            bulk_s2g(a.p.sP + row0, sm.sP(), st);
-            bulk_s2g(a.p.sQ + row0, sm.sQ(), st);
-            bulk_s2g(a.p.sV + row0, sm.sV(), st);
-        }
-        if (!direct) {
-            bulk_s2g(a.p.sWz + row0, sm.sWz(), sc);
-            bulk_s2g(a.p.counter + row0, sm.cnt(), i4);
-            if (a.auto_reset) bulk_s2g(a.p.ep_ret + row0, sm.ep(), i4);
-        }
-        if (full && !direct && !a.out_plain) {
-            if (a.reward) bulk_s2g(a.reward + row0, sm.rew(), sc);
-            if (a.terminated) bulk_s2g(a.terminated + row0, sm.term(), (uint32_t)T);
-            if (a.truncated) bulk_s2g(a.truncated + row0, sm.trunc(), (uint32_t)T);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        bulk_tile_stats<R>(a, sm, bid, rows);
         if (a.tile_dep) {
             // Measured (profiles/r02/sweep_b6..b8.jsonl, unsafe experiments): waiting for the stores costs nothing; the claim
-            // (ATOMG + L1 invalidate) ~0.5 us and the release fence below (MEMBAR.ALL.GPU) ~0.6 us of an 8.6 us step.  A relaxed
-            // publish would be faster and is not a release pattern: the next step of this tile could then read stale state.
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the tile is in global memory: publish it
-            tile_publish(a.tile_seq + (int64_t)bid * 4);
+            // (ATOMG + L1 invalidate) ~0.5 us and the release fence below (MEMBAR.ALL.GPU) ~0.6 us of an 8.6 us one-tile step.  A
+            // relaxed publish alone is not a release pattern: the next step of a tile could then read stale state.
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the CTA's last tile is in global memory: publish it
+            int last = tile0;
+#pragma unroll 1
+            for (int it = 1; it < tpc; ++it)
+                if (tile0 + it * (int)gridDim.x < tile_end) last = tile0 + it * (int)gridDim.x;
+            tile_publish(a.tile_seq + (int64_t)last * 4);
+            if (a.timeline) a.timeline[(int64_t)last * 8 + 7] = gtime();
         } else {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (a.timeline) a.timeline[(int64_t)tile0 * 8 + 7] = gtime();
         }
-        if (a.timeline) a.timeline[(int64_t)bid * 8 + 7] = gtime();
     }
     if (!a.pdl_trigger_early) pdl_launch_dependents();
     if (a.tile_dep) pdl_wait();             // keep stream order transitive (see gpd::step_kernel)
