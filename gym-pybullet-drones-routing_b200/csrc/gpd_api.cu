@@ -528,12 +528,12 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     const bool lean = rpm_like && cfg->physics_flags == 0;
     int P0 = 64;
     if (N == 1) P0 = (A == 4 && (f64 || !lean)) ? 128 : 64;      // A < 4: the 32 funnel-copy lanes limit the tile to 64 rows
+    else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 64 : 224;     // downwash: two block barriers per substep favour small CTAs
+                                                                // (512 envs x 64 drones: 17.4 us at 64 threads, 24.1 at 128)
     // lean FP32 sims on the bulk kernel: 128-env tiles in the range where launches are sequenced per tile and still give every SM
     // two CTAs of two tiles each (profiles/r02/sweep_b14/b16.jsonl, two tiles per CTA: 65,536 envs 7.74 us with 128-env tiles,
     // 8.12 us with 64; 16,384 envs 3.42 vs 3.28 us; 262,144 envs equal; 524,288 envs 68.4 vs 65.5 us, 1 M envs 124.6 vs 121.9 us)
     if (N == 1 && A == 4 && !f64 && lean && !ctrl && s->D >= 4 * 148 * 64 && s->D <= 262144) P0 = 128;
-    else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 64 : 224;     // downwash: two block barriers per substep favour small CTAs
-                                                                // (512 envs x 64 drones: 17.4 us at 64 threads, 24.1 at 128)
     Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0);
     // a history tile beyond the shared-memory limit (e.g. 256 drones per env with a 60-slot ring): register-copy path instead
     if (L.smem > (size_t)smem_optin) L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0, false);
