@@ -5,13 +5,16 @@
 // kernel moves this launch's bytes in 7.0 us; the step's own 14 address streams accessed per thread take 12.2 us; the same
 // streams moved only by cp.async.bulk take 7.1 us.  The per-thread / TMA-box mix of gpd::step_kernel sits at 9.3 us.
 //
-// One CTA = one tile of T = DPB envs, T threads, no DMA warp.  Thread 0 claims the tile (per-CTA step sequencing, see
+// One tile = T = DPB envs, T threads per CTA, no DMA warp.  Thread 0 claims the tile (per-tile step sequencing, see
 // gpd_kernels.cuh) and issues, on ONE mbarrier,
 //     the observation tile   T rows x W floats, CONTIGUOUS in global memory, read from obs_prev at +A floats: in shared
 //                            memory row r then holds [old kin[4..11] | old ring slots 1..B-1 | 16 stray bytes], i.e. the
 //                            shifted ring already sits where the new row wants it (BaseRLAviary.py:187,317-318)
-//     the state tiles        sP, sQ, sV (16/32 B per env), sWz, step counter, episode return
-//     the action tile        T x 16 B
+//     (bulk_direct < 2)      the state tiles sP, sQ, sV (16/32 B per env); (bulk_direct == 0) sWz, step counter, episode
+//                            return and the action tile too — by default (bulk_direct = 2) every thread fetches those itself
+//                            and only the observation tile occupies shared memory (BulkSmem)
+// A CTA runs one tile, or two one after the other through the same buffer in launches chained behind another handle
+// (step_kernel_bulk below).
 // Actions narrower than a float4 (ActionType.PID: A = 3, ONE_D_*: A = 1; rows still 16-byte granular): a bulk copy cannot
 // shift by 12 bytes, so the tile is loaded UNSHIFTED and every thread slides its own row by A floats inside shared memory
 // (aligned float4 reads, a register funnel, aligned float4 writes, in place and conflict-free: consecutive rows start 21 or
@@ -20,8 +23,8 @@
 // Every thread then integrates its drone exactly as gpd::step_kernel does (same device functions, same order of
 // operations: bit-identical in FP64; in FP32 the two kernels may differ in the compiler's FMA contraction, which is why a
 // handle never switches kernels between steps), patches its row (12 kin floats in front, this step's action in the newest
-// slot), writes its state / reward / flags back into shared memory; after one barrier thread 0 stores every tile back with
-// bulk copies (the observation tile as ONE contiguous 18 KB store).  Reading the full old rows costs 48 B per env more than
+// slot) and writes its state / reward / flags (to global memory, or back into shared memory when staged); after one barrier
+// thread 0 stores what is staged with bulk copies (the observation tile as ONE contiguous store: 18 KB per 64 envs).  Reading the full old rows costs 48 B per env more than
 // the shifted slots alone (the DRAM atom is 64 B: 32 of them were being fetched anyway); in exchange every byte moves in
 // long contiguous bursts.
 #pragma once
