@@ -2,7 +2,7 @@
 """Throughput of the other BASELINE.json shapes (parity-test configs, not bench lines), one GPU, CUDA-graph replay,
 rotating env sets sized to exceed the 126 MB L2.  Algorithmic bytes per env-ctrl-step from SURVEY §8d.
 
-    python profiles/configs.py [name ...] > profiles/r01/configs.jsonl
+    python profiles/configs.py [name ...] > profiles/rNN/configs.jsonl
 """
 import json
 import os
@@ -27,6 +27,7 @@ def measure(make_env, make_action, nsets, reps, trials=3):
     acts = [make_action(envs[0], k) for k in range(2 * nsets)]
     for e in envs:
         e.reset()
+        e._sim.set_step_chaining(True)      # the action buffers are generated before the first step is enqueued (gpd.h)
     period = 2 * nsets
 
     def cycle():
