@@ -530,6 +530,15 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     if (N == 1) P0 = (A == 4 && (f64 || !lean)) ? 128 : 64;      // A < 4: the 32 funnel-copy lanes limit the tile to 64 rows
     else P0 = (cfg->physics_flags & GPD_PHY_DW) ? 64 : 224;     // downwash: two block barriers per substep favour small CTAs
                                                                 // (512 envs x 64 drones: 17.4 us at 64 threads, 24.1 at 128)
+    // multi-drone RL envs without downwash run the bulk kernel (tiles of at most 128 drones, whole envs): that fixes the tile
+    // size, the wave search below is for gpd::step_kernel
+    bool multi_bulk = false;
+    {
+        const char* bv = getenv("GPD_BULK");
+        multi_bulk = N > 1 && N <= 128 && !ctrl && !(cfg->physics_flags & GPD_PHY_DW) && (12 + A * (cfg->ctrl_freq / 2)) % 4 == 0 &&
+                     (bv ? atoi(bv) != 0 : (12 + A * (cfg->ctrl_freq / 2)) * 4 <= 512);
+        if (multi_bulk) P0 = 128;
+    }
     // lean FP32 sims on the bulk kernel: 128-env tiles in the range where launches are sequenced per tile and still give every SM
     // two CTAs of two tiles each (profiles/r02/sweep_b14/b16.jsonl, two tiles per CTA: 65,536 envs 7.74 us with 128-env tiles,
     // 8.12 us with 64; 16,384 envs 3.42 vs 3.28 us; 262,144 envs equal; 524,288 envs 68.4 vs 65.5 us, 1 M envs 124.6 vs 121.9 us)
@@ -537,7 +546,7 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
     Layout L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0);
     // a history tile beyond the shared-memory limit (e.g. 256 drones per env with a 60-slot ring): register-copy path instead
     if (L.smem > (size_t)smem_optin) L = make_layout(cfg->threads_per_block ? cfg->threads_per_block : P0, false);
-    if (!cfg->threads_per_block) {
+    if (!cfg->threads_per_block && !multi_bulk) {
         // Wave quantisation: a launch of 1..4 waves pays for its partly filled last wave (MultiHover x2 FP32 at 32,768
         // envs: 512 CTAs on 444 slots = 28.5 us, 293 CTAs on 296 slots = 19.5 us).  Take the block size with the fewest
         // waves; the default wins ties.
@@ -597,7 +606,8 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         s->bulk_tpc = (!f64 && L.grid >= 3 * 148) ? 2 : 1;
         if (const char* tv = getenv("GPD_BULK_TPC")) s->bulk_tpc = atoi(tv) < 1 ? 1 : (atoi(tv) > GPD_BULK_MAX_TPC ? GPD_BULK_MAX_TPC : atoi(tv));
         const size_t bsm = (size_t)DPB * s->W * 4 + (direct >= 2 ? 0 : 3 * (size_t)DPB * 4 * rs) +
-                           (direct ? 0 : (size_t)DPB * 16 + 2 * (size_t)DPB * rs + 2 * (size_t)DPB * 4 + 2 * (size_t)DPB) + 8 * 32;
+                           (direct ? 0 : (size_t)DPB * 16 + 2 * (size_t)DPB * rs + 2 * (size_t)DPB * 4 + 2 * (size_t)DPB) + 8 * 32 +
+                           (N > 1 ? 2 * (size_t)DPB * rs + (size_t)DPB * 4 + (size_t)(DPB / N) * 4 + 16 : 0);     // per-env reduction scratch
         // Eligible: single-drone RL env, 4-wide actions, whole-float4 rows, 16-row-aligned tiles that fit shared memory.
         // Default on for rows of at most 512 bytes (30 Hz: W = 72, 48 Hz: W = 108): measured 9.2 -> 8.6 us (FP32),
         // 16.1 -> 13.3 us (FP64) at 65,536 envs, 131 -> 121 us at 1 M envs, and at 48 Hz 11.35 -> 10.79 us once the state
@@ -605,10 +615,13 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         // (60 Hz and up) leave too few tiles per SM.  GPD_BULK=1 forces it where eligible, GPD_BULK=0 turns it off.
         const char* ev = getenv("GPD_BULK");
         // narrower actions (PID: A = 3, ONE_D_*: A = 1) slide their rows inside shared memory and take their actions per thread
-        const bool eligible = !ctrl && N == 1 && s->W % 4 == 0 && DPB % 16 == 0 && DPB <= 128 && bsm <= (size_t)smem_optin &&
-                              (A == 4 || direct == 2);
+        // multi-drone envs (MultiHover) too, unless downwash is on (two block barriers per substep: gpd::step_kernel); their
+        // per-env arrays are written by the env's first drone, so they need direct == 2 like the narrow actions
+        const bool eligible = !ctrl && s->W % 4 == 0 && DPB <= 128 && bsm <= (size_t)smem_optin &&
+                              (N == 1 ? DPB % 16 == 0 && (A == 4 || direct == 2)
+                                      : direct == 2 && DPB % N == 0 && !(cfg->physics_flags & GPD_PHY_DW));
         s->bulk_ok = eligible && (ev ? atoi(ev) != 0 : s->W * 4 <= 512);
-        s->lc_bulk.threads = DPB; s->lc_bulk.grid = L.grid; s->lc_bulk.smem = bsm; s->lc_bulk.pdl = 0;
+        s->lc_bulk.threads = (DPB + 31) / 32 * 32; s->lc_bulk.grid = L.grid; s->lc_bulk.smem = bsm; s->lc_bulk.pdl = 0;   // whole warps
     }
     {   // programmatic dependent launch: measured to help only launches of at most ~2 CTAs per SM (the CTA launch and the
         // parameter fetch overlap the previous kernel's tail); with a full wave the early-resident CTAs all issue their
@@ -623,8 +636,8 @@ int gpd_create(const gpd_config* cfg, gpd_sim** out)
         int bps;
         if (s->bulk_ok)
             bps = cfg->precision == GPD_F64
-                ? step_bulk_blocks_per_sm<double>(cfg->action_type, cfg->physics_flags, s->lc_bulk.threads, s->lc_bulk.smem)
-                : step_bulk_blocks_per_sm<float>(cfg->action_type, cfg->physics_flags, s->lc_bulk.threads, s->lc_bulk.smem);
+                ? step_bulk_blocks_per_sm<double>(cfg->action_type, cfg->physics_flags, N, s->lc_bulk.threads, s->lc_bulk.smem)
+                : step_bulk_blocks_per_sm<float>(cfg->action_type, cfg->physics_flags, N, s->lc_bulk.threads, s->lc_bulk.smem);
         else
             bps = cfg->precision == GPD_F64
                 ? step_blocks_per_sm<double>(cfg->action_type, cfg->physics_flags, N, A, s->W, cfg->env_kind, s->lc.threads, s->lc.smem)

@@ -133,7 +133,7 @@ enum { GPD_K_FORCES = 0, GPD_K_LEAN = 1, GPD_K_PID = 2 };
 template <typename R> int step_blocks_per_sm(int action_type, int phy, int N, int A, int W, int env_kind, int threads, size_t smem);
 template <typename R> cudaError_t launch_step(const StepArgs<R>& a, const LaunchCfg& lc, const CUtensorMap* tm_prev,
                                               const CUtensorMap* tm_out, const CUtensorMap* tm_edge, cudaStream_t st);
-template <typename R> int step_bulk_blocks_per_sm(int action_type, int phy, int threads, size_t smem);
+template <typename R> int step_bulk_blocks_per_sm(int action_type, int phy, int N, int threads, size_t smem);
 template <typename R> cudaError_t launch_step_bulk(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
 template <typename R> cudaError_t launch_reset(const StepArgs<R>& a, const LaunchCfg& lc, cudaStream_t st);
 template <typename R> cudaError_t launch_get_state(const StepArgs<R>& a, const float* obs_latest, R* state20, R* rpy_rates, R* pid_state,

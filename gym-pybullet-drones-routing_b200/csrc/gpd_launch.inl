@@ -126,12 +126,12 @@ cudaError_t launch_step<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cons
     }
 }
 
-// ---- bulk-copy data path of the single-drone RL envs with 4-wide actions (gpd_step_bulk.cuh) ----
-template <int KIND>
+// ---- bulk-copy data path of the RL envs without downwash (gpd_step_bulk.cuh) ----
+template <int KIND, bool MULTI>
 static cudaError_t ensure_bulk_smem(size_t need)
 {
     static SmemLimit lim;
-    return lim.ensure(need, step_kernel_bulk<Real, KIND>);
+    return lim.ensure(need, step_kernel_bulk<Real, KIND, MULTI>);
 }
 
 static int bulk_kind(int action_type, int phy)
@@ -140,12 +140,12 @@ static int bulk_kind(int action_type, int phy)
     return !rpm_like ? GPD_K_PID : (phy == 0 ? GPD_K_LEAN : GPD_K_FORCES);
 }
 
-template <int KIND>
+template <int KIND, bool MULTI>
 static int bulk_occupancy_t(int threads, size_t smem)
 {
-    if (ensure_bulk_smem<KIND>(smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (ensure_bulk_smem<KIND, MULTI>(smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_kernel_bulk<Real, KIND>, threads, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_kernel_bulk<Real, KIND, MULTI>, threads, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -153,19 +153,23 @@ static int bulk_occupancy_t(int threads, size_t smem)
 }
 
 template <>
-int step_bulk_blocks_per_sm<Real>(int action_type, int phy, int threads, size_t smem)
+int step_bulk_blocks_per_sm<Real>(int action_type, int phy, int N, int threads, size_t smem)
 {
-    switch (bulk_kind(action_type, phy)) {
-    case GPD_K_FORCES: return bulk_occupancy_t<GPD_K_FORCES>(threads, smem);
-    case GPD_K_LEAN: return bulk_occupancy_t<GPD_K_LEAN>(threads, smem);
-    default: return bulk_occupancy_t<GPD_K_PID>(threads, smem);
+    const int k = bulk_kind(action_type, phy);
+    if (N > 1) {
+        if (k == GPD_K_FORCES) return bulk_occupancy_t<GPD_K_FORCES, true>(threads, smem);
+        if (k == GPD_K_LEAN) return bulk_occupancy_t<GPD_K_LEAN, true>(threads, smem);
+        return bulk_occupancy_t<GPD_K_PID, true>(threads, smem);
     }
+    if (k == GPD_K_FORCES) return bulk_occupancy_t<GPD_K_FORCES, false>(threads, smem);
+    if (k == GPD_K_LEAN) return bulk_occupancy_t<GPD_K_LEAN, false>(threads, smem);
+    return bulk_occupancy_t<GPD_K_PID, false>(threads, smem);
 }
 
-template <int KIND>
+template <int KIND, bool MULTI>
 static cudaError_t launch_step_bulk_t(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
 {
-    cudaError_t e = ensure_bulk_smem<KIND>(lc.smem);
+    cudaError_t e = ensure_bulk_smem<KIND, MULTI>(lc.smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)lc.grid);
@@ -177,17 +181,21 @@ static cudaError_t launch_step_bulk_t(const StepArgs<Real>& a, const LaunchCfg& 
     attr[0].val.programmaticStreamSerializationAllowed = lc.pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, step_kernel_bulk<Real, KIND>, a);
+    return cudaLaunchKernelEx(&cfg, step_kernel_bulk<Real, KIND, MULTI>, a);
 }
 
 template <>
 cudaError_t launch_step_bulk<Real>(const StepArgs<Real>& a, const LaunchCfg& lc, cudaStream_t st)
 {
-    switch (bulk_kind(a.action_type, a.phy)) {
-    case GPD_K_FORCES: return launch_step_bulk_t<GPD_K_FORCES>(a, lc, st);
-    case GPD_K_LEAN: return launch_step_bulk_t<GPD_K_LEAN>(a, lc, st);
-    default: return launch_step_bulk_t<GPD_K_PID>(a, lc, st);
+    const int k = bulk_kind(a.action_type, a.phy);
+    if (a.N > 1) {
+        if (k == GPD_K_FORCES) return launch_step_bulk_t<GPD_K_FORCES, true>(a, lc, st);
+        if (k == GPD_K_LEAN) return launch_step_bulk_t<GPD_K_LEAN, true>(a, lc, st);
+        return launch_step_bulk_t<GPD_K_PID, true>(a, lc, st);
     }
+    if (k == GPD_K_FORCES) return launch_step_bulk_t<GPD_K_FORCES, false>(a, lc, st);
+    if (k == GPD_K_LEAN) return launch_step_bulk_t<GPD_K_LEAN, false>(a, lc, st);
+    return launch_step_bulk_t<GPD_K_PID, false>(a, lc, st);
 }
 
 template <>

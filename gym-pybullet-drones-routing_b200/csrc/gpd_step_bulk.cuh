@@ -93,6 +93,10 @@ struct BulkSmem {
     __device__ uint8_t* trunc() const { return term() + T; }
     __device__ float* stat_f() const { return reinterpret_cast<float*>(direct ? after_state() : trunc() + T); }
     __device__ int* stat_i() const { return reinterpret_cast<int*>(stat_f() + 4 * 8); }      // up to 8 warps
+    // multi-drone envs (direct == 2 only): per-drone reward terms and flags for the in-order per-env sums, one done flag per env
+    __device__ R* red() const { return reinterpret_cast<R*>(stat_i() + 4 * 8); }             // [2 T]
+    __device__ int* redi() const { return reinterpret_cast<int*>(red() + 2 * T); }           // [T]
+    __device__ int* envf() const { return redi() + T; }                                      // [T / N]
 };
 
 // what a thread fetches itself before it waits for the tile (direct >= 1): issued right after the tile's dependency is
@@ -108,13 +112,16 @@ struct BulkPre {
 
 // One thread's share of a tile: state / action / counters from shared memory, the arithmetic of gpd::step_kernel, results
 // back into the tile (plus the few per-drone extras that live only in global memory).  `sub` = timeline slot or -1.
-template <typename R, int KIND>
+template <typename R, int KIND, bool MULTI>
 __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const BulkSmem<R>& sm, const BulkPre<R>& pre, int t,
                                                   int64_t row0, int rows, int tl)
 {
     constexpr bool LEAN = KIND == GPD_K_LEAN, HAS_PID = KIND == GPD_K_PID;
     const DevDrone<R>& P = a.drone;
-    const int64_t d = row0 + t;             // N == 1: drone = env
+    const int64_t d = row0 + t;             // drone; tiles hold whole envs (T and row0 are multiples of N)
+    const int le = MULTI ? t / a.N : t;     // env within the tile
+    const int i = MULTI ? t - le * a.N : 0; // drone within its env
+    const int64_t e = MULTI ? row0 / a.N + le : d;
     const bool active = t < rows;
     const bool full = rows == sm.T;
     // what does not come through shared memory: per-index constants and the optional per-drone extras
@@ -124,8 +131,8 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
     constexpr bool EARLY_CONST = !M<R>::is_double;      // FP64: fetched in the epilogue (register budget, see gpd::step_kernel)
     if (active) {
         if constexpr (EARLY_CONST) {
-            tg = a.p.target[a.target_per_env ? d : (int64_t)0];
-            if (pre_init) { ip0 = a.p.init_pos[0]; iq0 = a.p.init_quat[0]; }
+            tg = a.p.target[a.target_per_env ? d : (int64_t)i];
+            if (pre_init) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
         }
         if constexpr (!LEAN) {
             if (a.phy & GPD_PHY_DRAG) {
@@ -199,21 +206,46 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
     R rew;
     int term, trunc;
     if constexpr (!EARLY_CONST) {
-        if (active) tg = a.p.target[a.target_per_env ? d : (int64_t)0];
+        if (active) tg = a.p.target[a.target_per_env ? d : (int64_t)i];
     }
     {
         R ex = tg.x - s.px, ey = tg.y - s.py, ez = tg.z - s.pz;
         R dist = M<R>::sqrt(ex * ex + ey * ey + ez * ez);
         R d2 = dist * dist;
         R v = R(2) - d2 * d2;               // HoverAviary.py:78 / MultiHoverAviary.py:87
-        rew = v > R(0) ? v : R(0);
+        const R r_i = v > R(0) ? v : R(0);
         const R lim = a.env_kind == GPD_ENV_HOVER ? R(1.5) : R(2.0);
-        trunc = (M<R>::abs(s.px) > lim || M<R>::abs(s.py) > lim || s.pz > R(2.0) ||
-                 M<R>::abs(roll) > R(.4) || M<R>::abs(pitch) > R(.4)) ? 1 : 0;
-        term = dist < R(.0001);
+        const int tr_i = (M<R>::abs(s.px) > lim || M<R>::abs(s.py) > lim || s.pz > R(2.0) ||
+                          M<R>::abs(roll) > R(.4) || M<R>::abs(pitch) > R(.4)) ? 1 : 0;
+        if constexpr (MULTI) {              // in-order sums over the env's drones (MultiHoverAviary.py:86-88,103-105), as gpd::step_kernel
+            R* red = sm.red();
+            int* redi = sm.redi();
+            if (t < sm.T) { red[2 * t] = active ? r_i : R(0); red[2 * t + 1] = active ? dist : R(0); redi[t] = active ? tr_i : 0; }
+            __syncthreads();
+            rew = R(0); term = 0; trunc = 0;
+            if (active && i == 0) {
+                R rs = R(0), ds = R(0);
+                int tr = 0;
+                for (int j = 0; j < a.N; ++j) { rs += red[2 * (t + j)]; ds += red[2 * (t + j) + 1]; tr |= redi[t + j]; }
+                rew = rs;
+                term = a.env_kind == GPD_ENV_HOVER ? (red[2 * t + 1] < R(.0001)) : (ds < R(.0001));
+                trunc = tr;
+            }
+        } else {
+            rew = r_i; trunc = tr_i; term = dist < R(.0001);
+        }
     }
-    if (cnt > a.max_counter) trunc = 1;     // HoverAviary.py:114 (counter BEFORE the increment)
-    const int done = a.auto_reset ? (term | trunc) : 0;
+    if (i == 0 && cnt > a.max_counter) trunc = 1;     // HoverAviary.py:114 (counter BEFORE the increment)
+    int done = a.auto_reset ? (term | trunc) : 0;
+    if constexpr (MULTI) {
+        if (a.auto_reset) {                 // the env's flag to all of its drones
+            int* envf = sm.envf();
+            if (active && i == 0) envf[le] = done;
+            __syncthreads();
+            done = active ? envf[le] : 0;
+        }
+    }
+    const bool lead = active && i == 0;     // the thread that owns the env's reward, flags, counter and episode statistics
 
     float kin[12];
     kin[0] = (float)s.px; kin[1] = (float)s.py; kin[2] = (float)s.pz;
@@ -226,7 +258,7 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
     if (a.auto_reset) {                     // Monitor-style episode statistics, as in gpd::step_kernel
         float er = ep_ret0 + (float)rew;
         int el = cnt / a.S + 1;
-        const bool fin = active && done;
+        const bool fin = lead && done;
         const unsigned m = __ballot_sync(0xffffffffu, fin);
         float s1 = 0.f, s2 = 0.f;
         int nl = 0, nt = 0, mn = 0x7fffffff, mx = (int)0x80000000;
@@ -258,13 +290,13 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
             tk[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
         }
         if (pre_init) {                     // BaseAviary.reset -> _housekeeping (BaseAviary.py:451-491)
-            if constexpr (!EARLY_CONST) { ip0 = a.p.init_pos[0]; iq0 = a.p.init_quat[0]; }
+            if constexpr (!EARLY_CONST) { ip0 = a.p.init_pos[i]; iq0 = a.p.init_quat[i]; }
             s.px = ip0.x; s.py = ip0.y; s.pz = ip0.z;
             s.qx = iq0.x; s.qy = iq0.y; s.qz = iq0.z; s.qw = iq0.w;
             s.vx = s.vy = s.vz = R(0);
             s.wx = s.wy = s.wz = R(0);
         } else {
-            init_state(a, d, 0, s);
+            init_state(a, d, i, s);
         }
         quat_to_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
         avx = avy = avz = R(0);
@@ -289,8 +321,10 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
         const int32_t cnt_new = done ? 0 : cnt + a.S;                   // BaseAviary.py:382
         if (direct) {
             a.p.sWz[d] = s.wz;
-            a.p.counter[d] = cnt_new;
-            if (a.auto_reset) a.p.ep_ret[d] = ep_new;
+            if (lead) {
+                a.p.counter[e] = cnt_new;
+                if (a.auto_reset) a.p.ep_ret[e] = ep_new;
+            }
         } else {
             sm.sWz()[t] = s.wz;
             sm.cnt()[t] = cnt_new;
@@ -306,11 +340,11 @@ __device__ __forceinline__ void bulk_tile_physics(const StepArgs<R>& a, const Bu
         r[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
         if (full && !direct && !a.out_plain) {
             sm.rew()[t] = rew; sm.term()[t] = (uint8_t)term; sm.trunc()[t] = (uint8_t)trunc;
-        } else {                            // direct mode, caller arrays that are not 16-byte aligned (e.g. rows of a [T][E] uint8 trajectory
+        } else if (lead) {                  // direct mode, caller arrays that are not 16-byte aligned (e.g. rows of a [T][E] uint8 trajectory
                                             // buffer), or the ragged last tile (sizes are no multiples of 16 bytes): plain stores
-            if (a.reward) a.reward[d] = rew;
-            if (a.terminated) a.terminated[d] = (uint8_t)term;
-            if (a.truncated) a.truncated[d] = (uint8_t)trunc;
+            if (a.reward) a.reward[e] = rew;
+            if (a.terminated) a.terminated[e] = (uint8_t)term;
+            if (a.truncated) a.truncated[e] = (uint8_t)trunc;
         }
         if (!(LEAN && a.skip_aux)) {
             a.p.aux_av[d] = M<R>::make4(avx, avy, avz, R(0));
@@ -355,7 +389,7 @@ __device__ __forceinline__ void bulk_tile_stats(const StepArgs<R>& a, const Bulk
     }
 }
 
-template <typename R, int KIND>
+template <typename R, int KIND, bool MULTI>
 // registers: FP32 lean 64 (8 CTAs of 128 threads), DSLPID 80 (72 spilled once the tile loop was added), force models 80; FP64 128 — shared memory (26-53 KB per tile)
 // caps the FP64 variants at 512 threads per SM anyway, so they get the registers that would otherwise spill
 __global__ void __launch_bounds__(128, sizeof(R) == 4 ? (KIND == GPD_K_LEAN ? 8 : (KIND == GPD_K_PID ? 6 : 5)) : 4)
@@ -459,8 +493,9 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
                 if (a.A > 2) pre.act.z = __ldg(ap + 2);
             }
             pre.wz = a.p.sWz[d];
-            pre.cnt = a.p.counter[d];
-            if (a.auto_reset) pre.ep = a.p.ep_ret[d];
+            const int64_t e = MULTI ? d / a.N : d;      // every drone of an env reads the env's counter / return (one address per env)
+            pre.cnt = a.p.counter[e];
+            if (a.auto_reset) pre.ep = a.p.ep_ret[e];
             if (direct >= 2) { pre.p4 = a.p.sP[d]; pre.q4 = a.p.sQ[d]; pre.v4 = a.p.sV[d]; }
         }
         if (!a.obs_prev && t < rows) {          // no previous observation: all-zero ring (BaseRLAviary.py:153-154)
@@ -476,7 +511,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
         mbar_wait(&bar, (uint32_t)(it & 1));
         if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 2] = gtime();
 
-        bulk_tile_physics<R, KIND>(a, sm, pre, t, row0, rows, bid);
+        bulk_tile_physics<R, KIND, MULTI>(a, sm, pre, t, row0, rows, bid);
         fence_proxy_async_smem();               // this thread's shared-memory writes -> the bulk stores below
         __syncthreads();
         if (a.timeline && t == 0) a.timeline[(int64_t)bid * 8 + 4] = gtime();
@@ -501,7 +536,7 @@ step_kernel_bulk(const __grid_constant__ StepArgs<R> a)
                 if (a.truncated) bulk_s2g(a.truncated + row0, sm.trunc(), (uint32_t)T);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            bulk_tile_stats<R>(a, sm, bid, rows);
+            bulk_tile_stats<R>(a, sm, bid, MULTI ? rows / a.N : rows);
         }
     }
 

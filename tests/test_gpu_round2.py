@@ -366,6 +366,9 @@ print("rank", rank, "ok")
 
 
 @pytest.mark.parametrize("act,flags,precision,freq,E,direct", [
+    # multi-drone envs (MultiHover, in-order per-env sums through shared memory): N rides in the act string as "rpm*3"
+    ("rpm*2", 0, "f64", 30, 300, 2), ("rpm*2", 3, "f64", 30, 257, 2), ("rpm*3", 1, "f64", 48, 101, 2), ("pid*2", 0, "f64", 48, 90, 2),
+    ("rpm*5", 2, "f32", 30, 77, 2), ("vel*2", 0, "f64", 30, 64, 2),
     ("rpm", 0, "f64", 30, 1000, 2), ("rpm", 0, "f64", 48, 333, 2), ("rpm", 3, "f64", 30, 200, 2), ("vel", 0, "f64", 48, 777, 2),
     ("vel", 2, "f64", 48, 130, 2), ("rpm", 0, "f64", 240, 4096, 2), ("rpm", 0, "f32", 30, 1000, 2), ("rpm", 3, "f32", 30, 517, 2),
     ("vel", 0, "f32", 48, 300, 2),
@@ -382,9 +385,11 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
     kernels): agreement to a few ulp over a short open-loop horizon; the ring part of the observation is always exact."""
     rng = np.random.default_rng(12)
     f64 = precision == "f64"
-    kw = _kw("hover", act, 1, freq, flags, model=DroneModel.CF2P if act == "vel" else DroneModel.CF2X)
-    xyz = rng.uniform([-1, -1, 0.2], [1, 1, 1.5], size=(E, 1, 3))
-    rpy = rng.uniform(-0.2, 0.2, size=(E, 1, 3))
+    act, _, n = act.partition("*")
+    N = int(n or 1)
+    kw = _kw("hover" if N == 1 else "multihover", act, N, freq, flags, model=DroneModel.CF2P if act == "vel" else DroneModel.CF2X)
+    xyz = rng.uniform([-1, -1, 0.2], [1, 1, 1.5], size=(E, N, 3))
+    rpy = rng.uniform(-0.2, 0.2, size=(E, N, 3))
     kw["init_xyz"], kw["init_rpy"] = xyz, rpy
     monkeypatch.setenv("GPD_BULK", "1")           # force the bulk path also where the default would not pick it (240 Hz rows)
     monkeypatch.setenv("GPD_BULK_DIRECT", str(direct))
@@ -409,14 +414,14 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
             close(u, v, tag)
     # a first step with NO previous observation (all-zero ring), then the regular chain
     A = bulk.A
-    a0 = torch.from_numpy(rng.uniform(-1, 1, (E, 1, A)).astype(np.float32)).cuda()
+    a0 = torch.from_numpy(rng.uniform(-1, 1, (E, N, A)).astype(np.float32)).cuda()
     for sim in (bulk, ref):
         sim._have_prev = False
     for u, v in zip(bulk.step(a0)[:2], ref.step(a0)[:2]):
         close(u, v, "first step")
     same("first step")
     for t in range(40 if f64 else 8):
-        a = torch.from_numpy(rng.uniform(-1, 1, (E, 1, A)).astype(np.float32)).cuda()
+        a = torch.from_numpy(rng.uniform(-1, 1, (E, N, A)).astype(np.float32)).cuda()
         ob, oref = bulk.step(a), ref.step(a)
         for u, v in zip(ob[:2], oref[:2]):
             close(u, v, t)
@@ -432,7 +437,9 @@ def test_cuda_bulk_copy_path_matches_the_per_thread_path(act, flags, precision, 
     same("end")
     if f64:
         sb, sr = bulk.episode_stats(), ref.episode_stats()
-        assert np.array_equal(sb, sr) and (sb[0] > 0 or freq == 240)
+        # counts exactly; the float32 partial sums of the returns are grouped by warp, and the two kernels tile the envs differently
+        assert np.array_equal(sb[[0, 2, 6, 7]], sr[[0, 2, 6, 7]]) and (sb[0] > 0 or freq == 240)
+        assert np.allclose(sb[[1, 3]], sr[[1, 3]], rtol=1e-6, atol=0) and np.array_equal(sb[[4, 5]], sr[[4, 5]])
     bulk.close(); ref.close()
 
 
