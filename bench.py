@@ -684,10 +684,11 @@ def b200_arm(a):
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_note": (tr or {}).get("note"),
                 "traffic_steady_state": ((tr or {}).get("steady_state_bytes_per_env_step") or 0) * E or None,
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel_bulk<%s,LEAN>" % ("double" if a.precision == "f64" else "float"),
+                "algorithmic_bytes_per_launch": algo * E if algo else None, "kernel": "gpd::step_kernel_bulk<%s,LEAN,N=1>" % ("double" if a.precision == "f64" else "float"),
                 "kernel_ms_per_launch": per_launch_ms,
-                "note": "consecutive launches overlap across the kernel boundary (programmatic dependent launch + per-CTA step "
-                        "sequencing): kernel_ms_per_launch is the steady-state time per launch on ONE stream, not one launch's span"}
+                "note": "consecutive launches overlap across the kernel boundary (chained stepping: programmatic dependent launch + "
+                        "per-tile acquire/release sequencing, two tiles per CTA): kernel_ms_per_launch is the time per launch on ONE "
+                        "stream over the timed window, not one launch's span"}
         if nstreams > 1:
             roof["note"] = (f"{nstreams} streams: launches of independent env sets overlap, so kernel_ms_per_launch is the "
                             "throughput-equivalent time per launch, not one launch's duration")
