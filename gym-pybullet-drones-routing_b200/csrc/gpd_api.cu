@@ -237,6 +237,7 @@ static void fill_drone(const gpd_drone_params& p, DevDrone<R>& d)
     d.GND_EFF_COEFF = (R)p.GND_EFF_COEFF; d.PROP_RADIUS = (R)p.PROP_RADIUS; d.GND_EFF_H_CLIP = (R)p.GND_EFF_H_CLIP;
     for (int i = 0; i < 4; ++i) for (int k = 0; k < 3; ++k) d.ROTOR[i][k] = (R)p.ROTOR_XYZ[i][k];
     d.DW1 = (R)p.DW_COEFF_1; d.DW2 = (R)p.DW_COEFF_2; d.DW3 = (R)p.DW_COEFF_3;
+    d.DW1_NEG_PR2_16 = (R)(-p.DW_COEFF_1 * (p.PROP_RADIUS * 0.25) * (p.PROP_RADIUS * 0.25));
     d.KF_d = p.KF; d.KM_d = p.KM; d.GRAVITY_d = p.GRAVITY; d.L_d = p.L; d.ARM_d = p.L / std::sqrt(2.0);
     d.HOVER_RPM_d = p.HOVER_RPM; d.MAX_RPM_d = p.MAX_RPM;
     d.DT_INV_M = (R)0; d.DT_JINV[0] = d.DT_JINV[1] = d.DT_JINV[2] = (R)0;

@@ -42,6 +42,7 @@ struct DevDrone {
     R ROTOR[4][3];
     R DRAG[3];
     R DW1, DW2, DW3;
+    R DW1_NEG_PR2_16;       // -DW1 * (PROP_RADIUS / 4)^2, folded on the host in double (FP32 downwash pair)
 };
 
 template <typename R>

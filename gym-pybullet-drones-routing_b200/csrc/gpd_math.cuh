@@ -294,11 +294,19 @@ __device__ __forceinline__ R downwash_pair(const DevDrone<R>& P, R mx, R my, R m
         const float beta = fmaf(P.DW2, delta_z, P.DW3);
         const float zb = delta_z * beta;
         const float r = rcp_approx(zb);
-        const float rz = (P.PROP_RADIUS * 0.25f) * (r * beta);
-        const float ib = r * delta_z;
+        const float rb = r * beta;                                                         // 1 / delta_z
+        const float ib = r * delta_z;                                                      // 1 / beta
         const float e = ex2_approx(-0.72134752044448170368f * d2 * (ib * ib));            // exp(-0.5 u^2)
-        const float f = -P.DW1 * (rz * rz) * e;
-        return (delta_z > 0.f && d2 < 100.f && fabsf(zb) > 1e-30f) ? f : 0.f;
+        const float f = P.DW1_NEG_PR2_16 * (rb * rb) * e;                                  // -DW1 * (PROP_RADIUS / 4)^2 / delta_z^2 * e
+        // ONE predicate for the three guards (chained setp) and one select: the compiler's own lowering spends three selects
+        float out;
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.gt.f32 p, %1, 0f00000000;\n\t"
+            "setp.lt.and.f32 p, %2, 0f42C80000, p;\n\t"          // 100.0
+            "setp.gt.and.f32 p, %3, 0f0DA24260, p;\n\t"          // 1e-30
+            "selp.f32 %0, %4, 0f00000000, p;\n\t}"
+            : "=f"(out) : "f"(delta_z), "f"(d2), "f"(fabsf(zb)), "f"(f));
+        return out;
     }
 }
 
