@@ -373,7 +373,7 @@ def other_configs(torch, timer, world, rank, local, peak):
                                                              initial_xyzs=xyz, precision="f32", device=local),
                            lambda env, k: (env.HOVER_RPM * (1 + 0.02 * rand((El, N, 4), k))).float(), nsets=4, steps=16)
         pairs = Etot * N * N * r["S"] / (r["us_per_step"] * 1e-6)      # job-wide pair evaluations per second
-        instr_per_pair, mufu_per_pair = 23, 2                             # SASS count of downwash_pair, FP32
+        instr_per_pair, mufu_per_pair = 22, 2                             # SASS count of downwash_pair, FP32
         fi = pairs * instr_per_pair / (world * ISSUE_PEAK_FFMA_LANE_OPS)
         r.update(workload="C4 CtrlAviary 4,096 envs x 64 drones in total DYN+DW f32 240/48 (O(N^2) downwash)", scaling="strong",
                  envs_this_rank=El, drone_substeps_per_s=Etot * N * r["S"] / (r["us_per_step"] * 1e-6), pair_evals_per_s=pairs,

@@ -380,8 +380,11 @@ __device__ __forceinline__ void step_substep(const StepArgs<R>& a, State<R>& s, 
         }
         if constexpr (MULTI) {
             if (a.phy & GPD_PHY_DW) {                        // :362,367 against the substep-start snapshot
+                // FP32: x and y enter the snapshot pre-scaled (downwash_pair<R, true>): one multiply less in each of the N pairs
+                constexpr bool SC = !M<R>::is_double;
+                const R sx = SC ? s.px * R(GPD_DW_XY_SCALE) : s.px, sy = SC ? s.py * R(GPD_DW_XY_SCALE) : s.py;
                 phys_sync(nphys);
-                if (t < a.DPB) snap[t] = M<R>::make4(s.px, s.py, s.pz, R(0));   // (x, y, z, -): one 16/32-byte read per pair
+                if (t < a.DPB) snap[t] = M<R>::make4(sx, sy, s.pz, R(0));   // (x, y, z, -): one 16/32-byte read per pair
                 phys_sync(nphys);
                 R dw = R(0);
                 const V4<R>* env = snap + le * a.N;
@@ -389,7 +392,7 @@ __device__ __forceinline__ void step_substep(const StepArgs<R>& a, State<R>& s, 
 #pragma unroll 4
                     for (int j = 0; j < a.N; ++j) {
                         const V4<R> o = env[j];
-                        dw += downwash_pair(P, s.px, s.py, s.pz, o.x, o.y, o.z);
+                        dw += downwash_pair<R, SC>(P, sx, sy, s.pz, o.x, o.y, o.z);
                     }
                 }
                 fb[2] += dw;

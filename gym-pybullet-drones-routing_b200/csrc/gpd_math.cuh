@@ -270,7 +270,11 @@ __device__ __forceinline__ void drag_body(const DevDrone<R>& P, const R rpm_prev
 }
 
 // One pair term of BaseAviary._downwash (BaseAviary.py:799-804): body-z force on "me" from a drone at (ox,oy,oz).
-template <typename R>
+// XY_SCALED (FP32 step kernel): the caller passes x and y already multiplied by GPD_DW_XY_SCALE = sqrt(0.5 * log2(e)), so that the
+// squared horizontal distance arrives as the exponent's factor (one multiply less per pair; the drone scales its position once
+// per substep when it writes the env's snapshot).
+#define GPD_DW_XY_SCALE 0.84932180028801907f
+template <typename R, bool XY_SCALED = false>
 __device__ __forceinline__ R downwash_pair(const DevDrone<R>& P, R mx, R my, R mz, R ox, R oy, R oz)
 {
     R delta_z = oz - mz;                                                                   // :799
@@ -296,16 +300,17 @@ __device__ __forceinline__ R downwash_pair(const DevDrone<R>& P, R mx, R my, R m
         const float r = rcp_approx(zb);
         const float rb = r * beta;                                                         // 1 / delta_z
         const float ib = r * delta_z;                                                      // 1 / beta
-        const float e = ex2_approx(-0.72134752044448170368f * d2 * (ib * ib));            // exp(-0.5 u^2)
+        const float e = XY_SCALED ? ex2_approx(d2 * -(ib * ib))                            // d2 = 0.5 log2(e) dxy^2 already
+                                  : ex2_approx(-0.72134752044448170368f * d2 * (ib * ib)); // exp(-0.5 u^2)
         const float f = P.DW1_NEG_PR2_16 * (rb * rb) * e;                                  // -DW1 * (PROP_RADIUS / 4)^2 / delta_z^2 * e
         // ONE predicate for the three guards (chained setp) and one select: the compiler's own lowering spends three selects
         float out;
         asm("{\n\t.reg .pred p;\n\t"
             "setp.gt.f32 p, %1, 0f00000000;\n\t"
-            "setp.lt.and.f32 p, %2, 0f42C80000, p;\n\t"          // 100.0
+            "setp.lt.and.f32 p, %2, %5, p;\n\t"                  // dxy < 10
             "setp.gt.and.f32 p, %3, 0f0DA24260, p;\n\t"          // 1e-30
             "selp.f32 %0, %4, 0f00000000, p;\n\t}"
-            : "=f"(out) : "f"(delta_z), "f"(d2), "f"(fabsf(zb)), "f"(f));
+            : "=f"(out) : "f"(delta_z), "f"(d2), "f"(fabsf(zb)), "f"(f), "f"(XY_SCALED ? 72.134752044448170368f : 100.f));
         return out;
     }
 }
