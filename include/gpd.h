@@ -206,6 +206,12 @@ int gpd_reset_host(gpd_sim* sim, const uint8_t* env_mask, void* obs_out, void* s
  *                      on their own streams overlap one pool's H2D with another's D2H.
  *   gpd_reset_mirror   BaseAviary.reset for env_mask (HOST uint8 [E] or NULL = all): the ring survives (BaseRLAviary.py:153-154),
  *                      the window does not move, its 12 kin rows are refreshed.
+ *
+ * Zero-copy step: the log is mapped into the device's address space; when reward / terminated / truncated / terminal_kin are
+ * pinned host arrays too (cudaHostAlloc, cudaHostRegister, torch's pin_memory) the step kernel itself writes the kin rows and
+ * those arrays over PCIe, and reads `actions` from host memory if it is pinned (pageable actions are staged with one copy):
+ * one kernel launch per step, no separate copy operations. Arrays the device cannot address fall back to staging + copies;
+ * the results are the same either way.
  */
 int gpd_mirror_alloc(int64_t rows, int64_t row_len, float** log_out);
 int gpd_mirror_free(float* log);
