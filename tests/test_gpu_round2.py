@@ -517,3 +517,48 @@ def test_cuda_default_tile_sizes():
     assert tiles(65536, act="pid", freq=48, model=DroneModel.CF2P) == 1024        # 3-wide actions: 64-env tiles
     assert tiles(65536, "f64") == 512 and tiles(20000, "f64") == 157
     assert tiles(65536, flags=3) == 512                                            # force models: 128
+
+
+@pytest.mark.parametrize("E,precision,act", [(56923, "f32", "rpm"), (65536, "f32", "rpm"), (60000, "f32", "pid"), (40000, "f64", "rpm")])
+def test_cuda_two_tiles_per_cta_behind_another_handle(E, precision, act, monkeypatch):
+    """The benchmark's launch pattern: several handles stepped in rotation on one stream, chained.  A launch behind a step of
+    ANOTHER handle runs two tiles per CTA through one buffer (claims up front, a tile published under the next tile's loads;
+    FP32, >= 444 tiles) — here with an odd, ragged tile count too.  Against the same rotation launched serially
+    (GPD_TILE_DEP=0 GPD_PDL=0): identical bits in state, observation, reward, flags and statistics after 8 graph replays."""
+    rng = np.random.default_rng(9)
+    kw = _kw(act=act, freq=48 if act == "pid" else 30, model=DroneModel.CF2P if act == "pid" else DroneModel.CF2X)
+    nsets = 3
+    fast = [make_sim(kw, E, precision, auto_reset=True) for _ in range(nsets)]
+    for s_ in fast:
+        s_.set_step_chaining(True)
+    monkeypatch.setenv("GPD_TILE_DEP", "0"); monkeypatch.setenv("GPD_PDL", "0")
+    slow = [make_sim(kw, E, precision, auto_reset=True) for _ in range(nsets)]
+    monkeypatch.delenv("GPD_TILE_DEP"); monkeypatch.delenv("GPD_PDL")
+    A = fast[0].A
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (E, 1, A)).astype(np.float32)).cuda() for _ in range(5)]
+    outs = []
+    for sims in (fast, slow):
+        for s_ in sims:
+            s_.reset()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for k in range(4 * nsets):           # an even number of steps per handle: the ping-pong is back where it started
+                    sims[k % nsets].step(acts[k % 5])
+        for _ in range(8):
+            g.replay()
+        torch.cuda.synchronize()
+        res = []
+        for s_ in sims:
+            res += [x.clone() for x in s_.get_state()] + [s_.obs.clone(), s_.reward.clone(), s_.truncated.clone(),
+                                                            torch.from_numpy(s_.episode_stats())]
+        outs.append(res)
+
+    def bits(x):
+        return x.contiguous().view(torch.int64 if x.element_size() == 8 else (torch.int32 if x.element_size() == 4 else torch.uint8))
+    for x, y in zip(*outs):
+        assert torch.equal(bits(x), bits(y))
+    for s_ in fast + slow:
+        s_.close()
